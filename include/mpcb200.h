@@ -1,0 +1,146 @@
+/* mpcb200.h -- C ABI of libmpcb200.so: batched tracking-MPC solver for NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary for ONE hot path of medinammartin3/Safe-Autonomous-Driving-MPC: the per-timestep
+ * tracking MPC `TrajectoryTracker.solve(x0, obstacles)` (reference trajectory_tracking.py:213-263) together
+ * with the functions it evaluates (predict :87-114, cost :116-152, constraints :155-211, warm start :223-246)
+ * and the reference-signal table it queries (trajectory_loader.py:13-30, :64-102).
+ *
+ * The reference has no FFI of its own (it is pure Python); these entry points are what a ctypes binding on
+ * the reference side would call -- see INTEGRATION.md for that stub.  Plain pointers and sizes only.
+ * All functions return 0 on success and a negative mpcb_status on failure; nothing throws or aborts.
+ * There is no CPU fallback: every compute entry point fails with MPCB_ERR_CUDA if no sm_100 device is usable.
+ */
+#ifndef MPCB200_H
+#define MPCB200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MPCB_HORIZON 5      /* N, trajectory_tracking.py:18 */
+#define MPCB_NU 10          /* 2N decision variables, row-major [u1_0,u2_0,...] (:69-85) */
+#define MPCB_MAX_OBS 2      /* ObstaclesFSM emits at most {car, light} (:330-374) */
+#define MPCB_MAX_CONS 45    /* 5*(7+MAX_OBS) rows of constraints_wrapper (:164-209) */
+
+typedef enum mpcb_status {
+  MPCB_OK = 0,
+  MPCB_ERR_INVALID = -1,    /* bad argument (null pointer, K < 2, B < 0, ...) */
+  MPCB_ERR_CUDA = -2,       /* CUDA runtime error; mpcb_last_cuda_error() has the text */
+  MPCB_ERR_NOMEM = -3,
+  MPCB_ERR_UNSUPPORTED = -4 /* parameter set outside what the kernel was compiled for (N != 5) */
+} mpcb_status;
+
+/* per-problem solver exit flags written to status_out */
+#define MPCB_SOLVED 0       /* SQP step and QP residuals under tolerance, all constraints satisfied */
+#define MPCB_MAXITER 1      /* iteration caps hit; returned point satisfies the constraints to feas_tol */
+#define MPCB_INFEASIBLE 2   /* infeasibility certificate, or returned point violates a constraint > feas_tol */
+
+/* Mirrors the attributes of TrajectoryTracker.__init__ (trajectory_tracking.py:12-47) one to one, followed by
+ * the solver controls of this implementation.  Fill with mpcb_default_params() first. */
+typedef struct mpcb_params {
+  double dt;                       /* :17  0.2 */
+  int N;                           /* :18  5 (only 5 is supported) */
+  double u_min[2], u_max[2];       /* :31-32 */
+  double vehicle_radius;           /* :33 */
+  double w_d, w_o, w_v, w_u1, w_u2;/* :36-40 */
+  double obstacle_safety_distance; /* :43 */
+  double max_time_2_obs;           /* :44 */
+  double wheelbase;                /* :45 */
+  double lane_width;               /* :46 */
+  double safe_lane_margin;         /* :47 */
+  double brake_lookahead;          /* :233  40.0 (literal in solve) */
+  double brake_guess;              /* :241  -2.0 (literal in solve) */
+  /* solver controls (no counterpart in the reference, which uses SLSQP ftol=1e-3/maxiter=15) */
+  int max_rounds;                  /* linearise->QP rounds, default 10 */
+  int max_segments;                /* ADMM segments per round, default 12 */
+  int segment_iters;               /* ADMM iterations per segment, default 10 */
+  double rho_lo, rho_hi, rho_init; /* per-row step-size ladder, defaults 0.1, 1e4, 1.0 (x10 per rung) */
+  double alpha;                    /* over-relaxation, default 1.6 */
+  double eps_prim, eps_dual;       /* QP residual tolerances (inf-norm), defaults 1e-9, 1e-8 */
+  double eps_infeas;               /* infeasibility-certificate tolerance, default 1e-4 */
+  double step_tol;                 /* SQP termination on |dU|_inf, default 1e-7 */
+  double feas_tol;                 /* constraint tolerance for flags / active set, default 1e-6 */
+} mpcb_params;
+
+typedef struct mpcb_ctx* mpcb_handle;
+typedef struct mpcb_table* mpcb_table_handle;
+
+/* Fill *p with the reference's constants and the default solver controls. */
+int mpcb_default_params(mpcb_params* p);
+
+/* Reference-signal table (host object, no GPU needed).  Replaces TrajectoryLoader.__init__'s table part
+ * (trajectory_loader.py:13-30, :64-77, :84).
+ * ref_X: [K][5] rows [s,d,o,k,v]; ref_U: [KU][2] rows [u1,u2] (KU = K-1 in the reference's files).
+ * Applies the strict-monotone repair of s (:27-30) and the "controls see the first min(K,KU) knots" rule (:73-77). */
+int mpcb_table_create(mpcb_table_handle* out, const double* ref_X, int K, const double* ref_U, int KU);
+int mpcb_table_destroy(mpcb_table_handle t);
+/* Scalar queries; replace TrajectoryLoader.get_state / get_control (trajectory_loader.py:86-102) for callers such
+ * as run_simulation's plant step (trajectory_tracking.py:404). */
+int mpcb_table_get_state(mpcb_table_handle t, double s, double out5[5]);
+int mpcb_table_get_control(mpcb_table_handle t, double s, double out2[2]);
+double mpcb_table_s_max(mpcb_table_handle t);
+int mpcb_table_knots(mpcb_table_handle t);
+
+/* Solver context on CUDA device `device`: uploads the table, derives the constants.
+ * Replaces TrajectoryTracker.__init__ (trajectory_tracking.py:12-47).  The table may be destroyed afterwards. */
+int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int device);
+int mpcb_destroy(mpcb_handle h);
+
+/* Solve B independent problems.  DEVICE pointers; asynchronous on `cuda_stream` (a cudaStream_t, may be 0).
+ *   x0      [B][5]             current states [s,d,o,k,v]
+ *   obs_sv  [B][MAX_OBS][2]    (s, v) per obstacle, first n_obs[b] entries used
+ *   n_obs   [B]                0..2
+ * outputs (any may be NULL except U_out):
+ *   U_out   [B][5][2]   optimal controls           Xpred_out [B][6][5]  predict(x0, U*)  (:261)
+ *   obj_out [B]         cost(U*)                   status_out [B]       MPCB_SOLVED / MAXITER / INFEASIBLE
+ *   iters_out [B][2]    {linearisation rounds, total ADMM iterations}
+ *   cmin_out [B]        min over constraints_wrapper(U*) rows (reference order and sign)
+ *   active_out [B]      bit r (r < 5*(7+n_obs)) set when constraint row r <= feas_tol; bit 45+i set when
+ *                       variable i sits on a bound (within feas_tol)
+ * Replaces TrajectoryTracker.solve (trajectory_tracking.py:213-263) for a batch. */
+int mpcb_solve_batch(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
+                     double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
+                     double* cmin_out, unsigned long long* active_out, void* cuda_stream);
+
+/* Same, with HOST buffers: copies inputs to the device, solves, copies results back and synchronises.
+ * Pinned buffers (mpcb_host_alloc) make the copies asynchronous DMA. */
+int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
+                          double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
+                          double* cmin_out, unsigned long long* active_out);
+
+/* Evaluate the model functions at given controls (no optimisation).  DEVICE pointers, async on stream.
+ *   U [B][10] -> Xpred_out [B][6][5] (predict), cost_out [B] (cost), cons_out [B][45] (constraints_wrapper rows,
+ *   first 5*(7+n_obs[b]) valid, rest NaN), lin_out [B][150] (the solver's linearisation at U, packed: Gauss-Newton
+ *   Hessian lower triangle [0:55), q = g - H U [55:65), d(d_j)/dU rows j=2..5 [65:105), d(o_j)/dU rows [105:145),
+ *   5 zeros), warm_out [B][10] (the warm start of :223-246, unclipped).  Any output may be NULL. */
+int mpcb_eval_batch(mpcb_handle h, int B, const double* x0, const double* U, const double* obs_sv,
+                    const int* n_obs, double* Xpred_out, double* cost_out, double* cons_out, double* lin_out,
+                    double* warm_out, void* cuda_stream);
+
+/* Pinned host memory helpers (cudaHostAlloc / cudaFreeHost). */
+int mpcb_host_alloc(void** ptr, unsigned long long bytes);
+int mpcb_host_free(void* ptr);
+/* Device memory helpers so that hosts without a tensor library can hold device buffers. */
+int mpcb_device_alloc(mpcb_handle h, void** ptr, unsigned long long bytes);
+int mpcb_device_free(mpcb_handle h, void* ptr);
+int mpcb_memcpy_h2d(mpcb_handle h, void* dst, const void* src, unsigned long long bytes);
+int mpcb_memcpy_d2h(mpcb_handle h, void* dst, const void* src, unsigned long long bytes);
+
+/* Device time in milliseconds of the kernel launched by the last mpcb_solve_batch* call on this handle
+ * (CUDA events on the launching stream; synchronises that stream). */
+int mpcb_last_kernel_ms(mpcb_handle h, float* ms);
+/* Number of kernels this library has launched on this handle since creation. */
+unsigned long long mpcb_launch_count(mpcb_handle h);
+
+/* FP64 FMA-pipe peak probe: runs a register-resident DFMA loop on the handle's device and returns
+ * the measured TFLOP/s (2 flop per DFMA).  Used by bench.py as the roofline denominator. */
+int mpcb_measure_fp64_peak(mpcb_handle h, double* tflops, float* ms);
+
+const char* mpcb_strerror(int code);
+const char* mpcb_last_cuda_error(void);
+int mpcb_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MPCB200_H */

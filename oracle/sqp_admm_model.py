@@ -324,3 +324,82 @@ def slsqp_exact(tab, x0, obs_sv, n_obs, U_start=None, ftol=1e-14, maxiter=300):
                    constraints={"type": "ineq", "fun": c, "jac": cj},
                    options={"ftol": ftol, "maxiter": maxiter, "disp": False})
     return sol
+
+
+# ----------------------------------------------------------------------------------------------
+# Algorithm v2 (the one the CUDA kernel implements): sigma = 0, single-vector ADMM state
+# v = z_relaxed + y/rho, per-row rho re-selected from the detected active set every segment.
+NRM2_FLOOR = 1e-2
+
+
+def seg_rho(qp, act, rho_lo, rho_hi):
+    nrm2 = np.maximum(np.sum(qp["A"] ** 2, axis=2), NRM2_FLOOR)
+    return np.where(act, rho_hi, rho_lo) / nrm2
+
+
+def admm_v(qp, z, y, rho, alpha, iters):
+    """sigma=0 OSQP iteration.  Returns x (last x~), z, y, rp, rd (inf-norm residuals of the last
+    iterate: rp = |A x - z|, rd = |P x + q + A'y| evaluated without P), dy (last y increment)."""
+    Pm, q, A, l, u = qp["P"], qp["q"], qp["A"], qp["l"], qp["u"]
+    K = Pm + np.einsum("bmi,bm,bmj->bij", A, rho, A)
+    Kinv = np.linalg.inv(K)
+    for _ in range(iters):
+        w = rho * z - y
+        x = np.einsum("bij,bj->bi", Kinv, np.einsum("bmi,bm->bi", A, w) - q)
+        zt = np.einsum("bmi,bi->bm", A, x)
+        zr = alpha * zt + (1 - alpha) * z
+        zn = np.clip(zr + y / rho, l, u)
+        dy = rho * (zr - zn)
+        # residuals of (x, zn, y+dy):  P x + q = A'(rho z - y) - A' rho zt
+        rd = np.max(np.abs(np.einsum("bmi,bm->bi", A, rho * (z - zt) + dy)), axis=1)
+        rp = np.max(np.abs(zt - zn), axis=1)
+        y = y + dy
+        z = zn
+    return x, z, y, rp, rd, dy
+
+
+def sqp_solve_v2(tab, x0, obs_sv, n_obs, max_rounds=10, seg_iters=10, max_segs=8, rho_mid=1.0,
+                 rho_lo=0.1, rho_hi=1e4, alpha=1.6, eps_p=1e-9, eps_d=1e-8, step_tol=1e-7,
+                 verbose=False):
+    B = x0.shape[0]
+    U = warm_start(tab, x0, obs_sv, n_obs)
+    z = None
+    y = np.zeros((B, M))
+    done = np.zeros(B, dtype=bool)
+    rounds = np.zeros(B, dtype=int)
+    iters_tot = np.zeros(B, dtype=int)
+    qp_ok = np.zeros(B, dtype=bool)
+    for r in range(max_rounds):
+        asm = assemble(tab, x0, U)
+        qp = build_qp(asm, x0, U, obs_sv, n_obs)
+        if z is None:
+            z = np.clip(np.einsum("bmi,bi->bm", qp["A"], U), qp["l"], qp["u"])
+        conv = done.copy()
+        x = U.copy()
+        for sgm in range(max_segs):
+            if r == 0 and sgm == 0:
+                rho = seg_rho(qp, np.zeros((B, M), bool), rho_mid, rho_mid)
+            else:
+                rho = seg_rho(qp, np.abs(y) > 1e-10, rho_lo, rho_hi)
+            xn, zn, yn, rp, rd, dy = admm_v(qp, z, y, rho, alpha, seg_iters)
+            run = ~conv
+            x = np.where(run[:, None], xn, x)
+            z = np.where(run[:, None], zn, z)
+            y = np.where(run[:, None], yn, y)
+            iters_tot += run * seg_iters
+            conv |= (rp <= eps_p) & (rd <= eps_d)
+            if conv.all():
+                break
+        step = np.max(np.abs(x - U), axis=1)
+        upd = ~done
+        U = np.where(upd[:, None], x, U)
+        qp_ok = np.where(upd, conv, qp_ok)
+        rounds += upd
+        done |= (step < step_tol) & conv
+        if verbose:
+            print(f"round {r}: step max {step.max():.2e} med {np.median(step):.2e} qp_conv {conv.mean():.3f} "
+                  f"done {done.mean():.3f} iters mean {iters_tot.mean():.1f}")
+        if done.all():
+            break
+    asm = assemble(tab, x0, U)
+    return dict(U=U, cost=asm["cost"], X=asm["X"], rounds=rounds, iters=iters_tot, done=done, qp_ok=qp_ok)

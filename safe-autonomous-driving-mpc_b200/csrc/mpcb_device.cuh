@@ -1,0 +1,177 @@
+// mpcb_device.cuh -- device-side model of the tracking MPC (one thread = one problem).
+//
+// What is computed follows the reference formulation exactly:
+//   rollout      trajectory_tracking.py:87-114   (explicit Euler, k_ref looked up at the predicted s)
+//   cost         trajectory_tracking.py:116-152
+//   constraints  trajectory_tracking.py:155-211  (row order kept for the outputs)
+//   warm start   trajectory_tracking.py:223-246
+//   table lookup trajectory_loader.py:86-102 + scipy interp1d linear rule
+// How it is computed is new: exact forward sensitivities instead of finite differences, a Gauss-Newton
+// linearise->QP loop instead of SLSQP, and an OSQP-style ADMM (sigma = 0, single-vector state, per-row
+// step-size ladder) for the QP.  Everything is fp64.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace mpcb {
+
+constexpr int NH = 5;     // horizon
+constexpr int NV = 10;    // decision variables
+constexpr int NTRI = 55;  // packed lower triangle of a 10x10 symmetric matrix
+constexpr int MAXRUNG = 8;
+constexpr double BIG = 1e30;
+
+__host__ __device__ constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+
+struct DevTable {
+  const double* s;   // [K]   strictly increasing knots
+  const double* y;   // [K][4] d,o,k,v
+  const double* u;   // [Ku][2] u1,u2 (defined on the first Ku knots)
+  int K, Ku;
+  double s_max;
+  double last[4];    // X_ref[-1][1:5], returned for s >= s_max
+};
+
+struct DevParams {
+  double h;
+  double umin[2], umax[2];
+  double wd, wo, wv, wu[2];
+  double obs_safe, tgap;
+  double sld;          // lane_width/2 - vehicle_radius - safe_lane_margin
+  double alpha_lane[3];// 0, wheelbase/2, wheelbase
+  double brake_lookahead, brake_guess;
+  int max_rounds, max_segments, segment_iters;
+  int n_rung, e_init;
+  double lad[MAXRUNG]; // step-size ladder rho_lo * fac^k (capped at rho_hi)
+  double lad_ratio[MAXRUNG]; // lad[k-1]/lad[k] (k>=1): rescale of (v - z) when a row moves up one rung
+  double relax;        // ADMM over-relaxation alpha
+  double eps_p, eps_d, eps_inf, step_tol, feas_tol;
+  double inrm_v[NH], inrm_r1[NH], inrm_r2[NH];  // 1/max(|a|^2, floor) of the constant-coefficient rows
+};
+
+// ------------------------------------------------------------------------------------------------
+// Reference-signal table.  searchsorted(side='left') clipped to [1, K-1], then the two-term formula.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int seg_index(const double* __restrict__ s, int K, double x) {
+  int lo = 0, hi = K;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (__ldg(s + mid) < x) lo = mid + 1; else hi = mid;
+  }
+  return min(max(lo, 1), K - 1);
+}
+
+// get_state(s)[1:5] and the slope of each column on the bracketing segment
+__device__ __forceinline__ void lookup_state(const DevTable& T, double s, double (&val)[4], double (&slope)[4]) {
+  if (s >= T.s_max) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { val[c] = T.last[c]; slope[c] = 0.0; }
+    return;
+  }
+  const int i = seg_index(T.s, T.K, s);
+  const double x_lo = __ldg(T.s + i - 1), x_hi = __ldg(T.s + i);
+  const double inv = 1.0 / (x_hi - x_lo);
+  const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
+  const double2* yl = reinterpret_cast<const double2*>(T.y + 4 * (i - 1));
+  const double2* yh = reinterpret_cast<const double2*>(T.y + 4 * i);
+  const double2 l0 = __ldg(yl), l1 = __ldg(yl + 1), h0 = __ldg(yh), h1 = __ldg(yh + 1);
+  const double ylo[4] = {l0.x, l0.y, l1.x, l1.y}, yhi[4] = {h0.x, h0.y, h1.x, h1.y};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    val[c] = wl * yhi[c] + wr * ylo[c];
+    slope[c] = (yhi[c] - ylo[c]) * inv;
+  }
+}
+
+__device__ __forceinline__ void lookup_control(const DevTable& T, double s, double (&u)[2]) {
+  if (s >= T.s_max) { u[0] = 0.0; u[1] = 0.0; return; }
+  const int i = seg_index(T.s, T.Ku, s);
+  const double x_lo = __ldg(T.s + i - 1), x_hi = __ldg(T.s + i);
+  const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
+  const double2 ul = __ldg(reinterpret_cast<const double2*>(T.u + 2 * (i - 1)));
+  const double2 uh = __ldg(reinterpret_cast<const double2*>(T.u + 2 * i));
+  u[0] = wl * uh.x + wr * ul.x;
+  u[1] = wl * uh.y + wr * ul.y;
+}
+
+// warm start, trajectory_tracking.py:223-246 (unclipped)
+__device__ __forceinline__ void warm_start(const DevTable& T, const DevParams& P, const double (&x0)[5],
+                                           const double (&obs)[2][2], int n_obs, double (&U)[NV]) {
+  double s_cur = x0[0];
+  const double v_cur = x0[4];
+  bool brake = false;
+#pragma unroll
+  for (int j = 0; j < NH; ++j) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (k < n_obs && (obs[k][0] - s_cur) < P.brake_lookahead) brake = true;
+    double ur[2];
+    lookup_control(T, s_cur, ur);
+    U[2 * j] = ur[0];
+    U[2 * j + 1] = brake ? P.brake_guess : ur[1];
+    s_cur += v_cur * P.h;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Values-only rollout: X[6][5], cost, and constraint rows in the reference's order.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rollout_values(const DevTable& T, const DevParams& P, const double (&x0)[5],
+                                               const double (&U)[NV], double (&X)[NH + 1][5], double& cost) {
+#pragma unroll
+  for (int c = 0; c < 5; ++c) X[0][c] = x0[c];
+  double val[4], slope[4];
+  double c_acc = 0.0;
+#pragma unroll
+  for (int j = 0; j < NH; ++j) {
+    const double s = X[j][0], d = X[j][1], o = X[j][2], k = X[j][3], v = X[j][4];
+    lookup_state(T, s, val, slope);
+    if (j > 0) {  // tracking terms of step j use the lookup at s_j
+      const double rd = d - val[0], ro = o - val[1], rv = v - val[3];
+      c_acc += P.wd * (rd * rd);
+      c_acc += P.wo * (ro * ro);
+      c_acc += P.wv * (rv * rv);
+    }
+    X[j + 1][0] = s + P.h * v;
+    X[j + 1][1] = d + P.h * (v * o);
+    X[j + 1][2] = o + P.h * (v * (k - val[2]));
+    X[j + 1][3] = k + P.h * U[2 * j];
+    X[j + 1][4] = v + P.h * U[2 * j + 1];
+  }
+  {
+    lookup_state(T, X[NH][0], val, slope);
+    const double rd = X[NH][1] - val[0], ro = X[NH][2] - val[1], rv = X[NH][4] - val[3];
+    c_acc += P.wd * (rd * rd);
+    c_acc += P.wo * (ro * ro);
+    c_acc += P.wv * (rv * rv);
+  }
+#pragma unroll
+  for (int j = 0; j < NH; ++j) {
+    c_acc += P.wu[0] * (U[2 * j] * U[2 * j]);
+    c_acc += P.wu[1] * (U[2 * j + 1] * U[2 * j + 1]);
+  }
+  cost = c_acc;
+}
+
+// constraint rows of constraints_wrapper (trajectory_tracking.py:171-207) for step j (1-based), written to
+// out[0 .. 6+n_obs]; returns the number of rows.
+__device__ __forceinline__ int constraint_rows(const DevParams& P, const double (&Xj)[5], int j,
+                                               const double (&obs)[2][2], int n_obs, double* out) {
+  const double s = Xj[0], d = Xj[1], o = Xj[2], v = Xj[4];
+  int r = 0;
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    const double val = d + P.alpha_lane[a] * o;
+    out[r++] = P.sld - val;
+    out[r++] = val + P.sld;
+  }
+  for (int k = 0; k < n_obs; ++k) {
+    const double s_obs = obs[k][0] + obs[k][1] * (j * P.h);
+    const double safe = fmax(P.obs_safe, v * P.tgap);
+    out[r++] = (s_obs - s) - safe;
+  }
+  out[r++] = v;
+  return r;
+}
+
+}  // namespace mpcb
