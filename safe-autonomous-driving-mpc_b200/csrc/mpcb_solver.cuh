@@ -590,6 +590,10 @@ __device__ __forceinline__ SolveOut solve_one(const DevTable& T, const DevParams
     }
   }
   if (infeasible) out.status = 2;
+  // the returned controls always respect the box (a no-op for converged problems; non-converged or infeasible
+  // ADMM iterates may sit slightly outside).  SLSQP treats the bounds as hard in the same way.
+#pragma unroll
+  for (int i = 0; i < NV; ++i) pb.U[i] = clipd(pb.U[i], P.umin[i & 1], P.umax[i & 1]);
   return out;
 }
 

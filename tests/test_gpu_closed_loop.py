@@ -1,0 +1,85 @@
+"""Closed-loop envelope: the GPU tracker dropped into the run_simulation loop
+(trajectory_tracking.py:377-443) against the unmodified reference's own closed-loop log (tests/golden/closed_loop_*).
+
+The reference stops SLSQP at ftol=1e-3 / 15 iterations, so its log is 2e-3..5e-2 away from its own converged optimum
+(SURVEY C4); the envelope below is ~2x the reference's measured loose-vs-tight spread and applies outside
+the windows where the reference problem is infeasible (red-light approach), where only verdicts are compared."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _verdicts(hx, hu, obs_s, tl, fsm, s_total):
+    """sanity_checks.py:79-184 as booleans (CPU-time item excluded)."""
+    v = {"destination": hx[-1, 0] >= s_total - 1.0, "on_road": np.max(np.abs(hx[:, 1])) <= 1.5,
+         "steer": not ((hu[:, 0].min() < -0.7) or (hu[:, 0].max() > 0.7)),
+         "accel": not ((hu[:, 1].min() < -5.1) or (hu[:, 1].max() > 4.1))}
+    if fsm.dynamic_obstacle:
+        obs_s = np.asarray(obs_s, dtype=float)
+        m = ~np.isnan(obs_s)
+        if m.any():
+            L = min(len(hx), len(obs_s))
+            v["obstacle"] = (obs_s[:L][m[:L]] - hx[:L, 0][m[:L]]).min() >= 1.0
+    if fsm.traffic_light:
+        idx = np.where(hx[:, 0] > fsm.tl_pos)[0]
+        v["light"] = not (len(idx) > 0 and idx[0] < len(tl) and tl[idx[0]] == "RED")
+    return v
+
+
+@pytest.mark.parametrize("i", [1, 2, 3])
+def test_closed_loop_envelope(i, gpu_trackers):
+    import safe_autonomous_driving_mpc_b200 as M
+    from safe_autonomous_driving_mpc_b200 import environment as E
+    z = golden(f"closed_loop_traj{i}")
+    L, T = gpu_trackers[i]
+    sc = {1: None, 2: E.SCENARIO_TRAJECTORY2, 3: E.SCENARIO_TRAJECTORY3}[i]
+    fsm = M.ObstaclesFSM(dynamic_obstacle=i > 1, traffic_light=i > 1, scenario=sc)
+    flags = []
+    hx, hu, ht, hp, hobs, htl, _ = M.run_simulation(T, fsm, L, record_flags=flags)
+    ref_x, ref_u = z["hist_x"], z["hist_u"]
+    # verdicts identical item by item
+    ref_fsm = M.ObstaclesFSM(dynamic_obstacle=i > 1, traffic_light=i > 1, scenario=sc)
+    ours = _verdicts(hx, hu, hobs, htl, fsm, L.s_max)
+    ref = _verdicts(ref_x, ref_u, z["hist_obs_s"], [str(t) for t in z["hist_tl"]], ref_fsm, L.s_max)
+    assert ours == ref
+    assert all(ours.values())
+    # step count: the reference's own tight-vs-loose runs give identical counts
+    n_ref = len(ref_u)
+    assert abs(len(hu) - n_ref) <= max(2, int(0.01 * n_ref)), (len(hu), n_ref)
+    # state envelope outside infeasible windows.  A stop at the red light shifts everything after it in TIME (the
+    # 20 s timer starts when v < 0.1, which the loose and the converged solver reach a step apart), so states are
+    # compared at equal arc length s, not at equal step index.
+    def windows(bad, n):
+        w = np.zeros(n, dtype=bool)
+        for t in np.where(bad)[0]:
+            w[max(0, t - 10): t + 60] = True          # infeasible step and the recovery after it
+        return w
+    st = np.array([f[0] for f in flags])
+    keep = ~windows(st != 0, len(hu))
+    keep_ref = ~windows(z["slsqp"][:, 0] != 0, n_ref)
+    if i == 1:
+        assert keep.all() and keep_ref.all()
+    assert keep.mean() > 0.8
+    rs = ref_x[:-1][keep_ref]
+    order = np.argsort(rs[:, 0])
+    rs, ru = rs[order], ref_u[keep_ref][order]
+    ours_x, ours_u = hx[:-1][keep], hu[keep]
+    inside = (ours_x[:, 0] >= rs[0, 0]) & (ours_x[:, 0] <= rs[-1, 0])
+    # only compare where the reference has a kept sample nearby (not across an excluded window)
+    j = np.clip(np.searchsorted(rs[:, 0], ours_x[:, 0]), 1, len(rs) - 1)
+    near = (rs[j, 0] - rs[j - 1, 0]) < 5.0
+    m = inside & near
+    assert m.mean() > 0.9
+    def at_s(col):
+        return np.interp(ours_x[m, 0], rs[:, 0], col)
+    dd = np.abs(ours_x[m, 1] - at_s(rs[:, 1]))
+    do = np.abs(ours_x[m, 2] - at_s(rs[:, 2]))
+    dv = np.abs(ours_x[m, 4] - at_s(rs[:, 4]))
+    assert dd.max() <= 0.1 and do.max() <= 0.08 and dv.max() <= 0.25, (dd.max(), do.max(), dv.max())
+    du = np.maximum(np.abs(ours_u[m, 0] - at_s(ru[:, 0])), np.abs(ours_u[m, 1] - at_s(ru[:, 1])))
+    assert np.quantile(du, 0.99) <= 0.5 and np.median(du) <= 0.02, np.quantile(du, [0.5, 0.9, 0.99])
+    # real-time budget of the reference's own sanity check (150 ms, sanity_checks.py:94) is met per solve
+    assert np.max(ht[5:]) * 1000 < 150.0
