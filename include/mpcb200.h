@@ -136,6 +136,49 @@ unsigned long long mpcb_launch_count(mpcb_handle h);
  * the measured TFLOP/s (2 flop per DFMA).  Used by bench.py as the roofline denominator. */
 int mpcb_measure_fp64_peak(mpcb_handle h, double* tflops, float* ms);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Planner function evaluation (north_star item (c)): the offline Hermite-Simpson NLP of trajectory_planning.py.
+ * The outer optimisation loop stays on the host; these entry points evaluate, for all collocation intervals of a
+ * batch of chunks at once, what the reference evaluates closure by closure with finite differences.
+ * k_ref(s) is the curvature column of the handle's reference-signal table with linear extrapolation
+ * (TrajectoryLoader.interp_k, trajectory_loader.py:69) -- the GraphHopper spline is not in the repository.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct mpcb_planner_params {
+  double dt;                       /* trajectory_planning.py:514  0.3 */
+  double w_y, w_s, w_u, w_slack;   /* :14   10, 10, 0.1, 100 */
+  double u_min[2], u_max[2];       /* :36-37 */
+  double k_min, k_max;             /* :44-45 */
+  double a_max;                    /* :48 */
+  int simpson_sign;                /* -1: x_pred = x_k - dt/6(...) as committed (:198); +1: the form the committed
+                                      trajectories satisfy */
+  double v_min, v_max;             /* constant speed limits used when no per-node arrays are passed (:465, :476) */
+  double s_total;                  /* route length used by the progress cost (:156-158) */
+} mpcb_planner_params;
+
+int mpcb_planner_default_params(mpcb_planner_params* p);
+
+/* Hermite-Simpson defects and their derivatives.  DEVICE pointers, async on `cuda_stream`.
+ *   z      [C][8N+5]    decision vectors in the reference layout [X (N+1)x5 ; U Nx2 ; S N] (:91-126)
+ *   lam    [C][N][5]    multipliers of the defect rows (required iff hess != NULL)
+ *   defect [C][N][5]    value of closure dynamics_constraints(z, k) (:183-208)
+ *   jac    [C][N][5][12]  d defect / d (x_k, x_{k+1}, u_k)                        (may be NULL)
+ *   hess   [C][N][12][12] d^2 (lam . defect) / d (x_k, x_{k+1}, u_k)^2            (may be NULL)
+ * Replaces the N `dynamics_constraints` closures and scipy's finite differences of them. */
+int mpcb_hs_eval(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int N, const double* z,
+                 const double* lam, double* defect, double* jac, double* hess, void* cuda_stream);
+
+/* Node-wise rows, stage costs and the cost gradient.  DEVICE pointers, async on `cuda_stream`.
+ *   s0         [C]            x0[0] of each chunk (normalisation of the progress cost, :156-157)
+ *   vmin_nodes, vmax_nodes [C][N+1]  v_min_fun(s_k), v_max_fun(s_k) evaluated by the host (NULL: constants from p)
+ *   node_rows  [C][N+1][6]    (v+slack)-v_min, v_max-(v+slack), a_max-k v^2, a_max+k v^2, k-k_min, k_max-k (:249-307)
+ *   ctrl_rows  [C][N][5]      u1-u1_min, u1_max-u1, u2-u2_min, u2_max-u2, slack                        (:310-347)
+ *   cost_terms [C][N]         stage costs; cost [C] = their sum in the reference's order               (:128-170)
+ *   cost_grad  [C][8N+5]      d cost / d z
+ * Any output may be NULL (cost needs cost_terms). */
+int mpcb_hs_nodes(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int N, const double* z, const double* s0,
+                  const double* vmin_nodes, const double* vmax_nodes, double* node_rows, double* ctrl_rows,
+                  double* cost_terms, double* cost, double* cost_grad, void* cuda_stream);
+
 const char* mpcb_strerror(int code);
 const char* mpcb_last_cuda_error(void);
 int mpcb_abi_version(void);

@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libmpcb200.so")
-SOURCES = ["mpcb_api.cu"]
-HEADERS = ["mpcb_device.cuh", "mpcb_solver.cuh"]
+SOURCES = ["mpcb_api.cu", "mpcb_planner.cu"]
+HEADERS = ["mpcb_device.cuh", "mpcb_solver.cuh", "mpcb_planner.cuh", "mpcb_internal.h"]
 
 
 def nvcc_path():

@@ -34,6 +34,20 @@ class Params(C.Structure):
     ]
 
 
+class PlannerParams(C.Structure):
+    """struct mpcb_planner_params (include/mpcb200.h); mirrors TrajectoryOptimizer.__init__,
+    trajectory_planning.py:14-48."""
+    _fields_ = [
+        ("dt", C.c_double),
+        ("w_y", C.c_double), ("w_s", C.c_double), ("w_u", C.c_double), ("w_slack", C.c_double),
+        ("u_min", C.c_double * 2), ("u_max", C.c_double * 2),
+        ("k_min", C.c_double), ("k_max", C.c_double), ("a_max", C.c_double),
+        ("simpson_sign", C.c_int),
+        ("v_min", C.c_double), ("v_max", C.c_double),
+        ("s_total", C.c_double),
+    ]
+
+
 # every symbol include/mpcb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mpcb_default_params": (C.c_int, [C.POINTER(Params)]),
@@ -57,6 +71,9 @@ SYMBOLS = {
     "mpcb_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mpcb_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "mpcb_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
+    "mpcb_planner_default_params": (C.c_int, [C.POINTER(PlannerParams)]),
+    "mpcb_hs_eval": (C.c_int, [C.c_void_p, C.POINTER(PlannerParams), C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
+    "mpcb_hs_nodes": (C.c_int, [C.c_void_p, C.POINTER(PlannerParams), C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_void_p]),
     "mpcb_strerror": (C.c_char_p, [C.c_int]),
     "mpcb_last_cuda_error": (C.c_char_p, []),
     "mpcb_abi_version": (C.c_int, []),

@@ -186,39 +186,19 @@ __global__ void __launch_bounds__(256) mpcb_dfma_probe(double* out, int iters, d
 // ================================================================================================
 using namespace mpcb;
 
-static thread_local char g_cuda_err[512] = "";
+#include "mpcb_internal.h"
+#include "mpcb_params.h"
 
-static int cuda_fail(cudaError_t e, const char* where) {
+thread_local char g_cuda_err[512] = "";
+
+int cuda_fail(cudaError_t e, const char* where) {
   snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", where, cudaGetErrorString(e));
   return MPCB_ERR_CUDA;
 }
-#define CK(call)                                        \
-  do {                                                  \
-    cudaError_t e_ = (call);                            \
-    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
-  } while (0)
-
-struct mpcb_ctx {
-  int device;
-  mpcb_params params;
-  DevParams dp;
-  DevTable dt;
-  int K, Ku;
-  double* d_s = nullptr;
-  double* d_y = nullptr;
-  double* d_u = nullptr;
-  // workspace for the host-buffer entry point
-  void* ws = nullptr;
-  size_t ws_bytes = 0;
-  cudaStream_t stream = nullptr;   // private stream of the *_host entry point
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-  bool timed = false;
-  unsigned long long launches = 0;
-};
 
 extern "C" {
 
-int mpcb_abi_version(void) { return 1; }
+int mpcb_abi_version(void) { return 2; }
 
 const char* mpcb_strerror(int code) {
   switch (code) {
@@ -235,66 +215,7 @@ const char* mpcb_last_cuda_error(void) { return g_cuda_err; }
 
 int mpcb_default_params(mpcb_params* p) {
   if (!p) return MPCB_ERR_INVALID;
-  memset(p, 0, sizeof(*p));
-  p->dt = 0.2; p->N = 5;
-  p->u_min[0] = -0.6; p->u_min[1] = -5.0; p->u_max[0] = 0.6; p->u_max[1] = 4.0;
-  p->vehicle_radius = 1.0;
-  p->w_d = 10.0; p->w_o = 10.0; p->w_v = 5.0; p->w_u1 = 0.5; p->w_u2 = 0.5;
-  p->obstacle_safety_distance = 5.0; p->max_time_2_obs = 1.5; p->wheelbase = 2.8; p->lane_width = 3.0;
-  p->safe_lane_margin = 0.1;
-  p->brake_lookahead = 40.0; p->brake_guess = -2.0;
-  p->max_rounds = 10; p->max_segments = 12; p->segment_iters = 10;
-  p->rho_lo = 0.1; p->rho_hi = 1e4; p->rho_init = 1.0;
-  p->alpha = 1.6;
-  p->eps_prim = 1e-9; p->eps_dual = 1e-8; p->eps_infeas = 1e-4;
-  p->step_tol = 1e-7; p->feas_tol = 1e-6;
-  return MPCB_OK;
-}
-
-static int derive_params(const mpcb_params& p, DevParams& d) {
-  if (p.N != NH) return MPCB_ERR_UNSUPPORTED;
-  if (!(p.dt > 0) || p.max_rounds < 1 || p.max_segments < 1 || p.segment_iters < 1) return MPCB_ERR_INVALID;
-  if (!(p.rho_lo > 0) || !(p.rho_hi >= p.rho_lo) || !(p.alpha > 0 && p.alpha < 2)) return MPCB_ERR_INVALID;
-  memset(&d, 0, sizeof(d));
-  d.h = p.dt;
-  for (int i = 0; i < 2; ++i) { d.umin[i] = p.u_min[i]; d.umax[i] = p.u_max[i]; }
-  d.wd = p.w_d; d.wo = p.w_o; d.wv = p.w_v; d.wu[0] = p.w_u1; d.wu[1] = p.w_u2;
-  d.obs_safe = p.obstacle_safety_distance; d.tgap = p.max_time_2_obs;
-  d.sld = p.lane_width / 2.0 - p.vehicle_radius - p.safe_lane_margin;   // trajectory_tracking.py:169
-  d.alpha_lane[0] = 0.0; d.alpha_lane[1] = p.wheelbase / 2.0; d.alpha_lane[2] = p.wheelbase;
-  d.brake_lookahead = p.brake_lookahead; d.brake_guess = p.brake_guess;
-  d.max_rounds = p.max_rounds; d.max_segments = p.max_segments; d.segment_iters = p.segment_iters;
-  const double fac = 10.0;
-  int n = 0;
-  double r = p.rho_lo;
-  while (n < MAXRUNG) {
-    d.lad[n++] = std::min(r, p.rho_hi);
-    if (r >= p.rho_hi) break;
-    r *= fac;
-  }
-  d.n_rung = n;
-  d.lad_ratio[0] = 1.0;
-  for (int k = 1; k < n; ++k) d.lad_ratio[k] = d.lad[k - 1] / d.lad[k];
-  int best = 0;
-  for (int k = 0; k < n; ++k)
-    if (fabs(log(d.lad[k] / p.rho_init)) < fabs(log(d.lad[best] / p.rho_init))) best = k;
-  d.e_init = best;
-  d.relax = p.alpha;
-  d.eps_p = p.eps_prim; d.eps_d = p.eps_dual; d.eps_inf = p.eps_infeas;
-  d.step_tol = p.step_tol; d.feas_tol = p.feas_tol;
-  const double h = p.dt, floor_ = NRM2_FLOOR;
-  for (int j = 1; j <= NH; ++j) {
-    double nv = 0, n1 = 0, n2 = 0;
-    for (int i = 0; i < j; ++i) {
-      const double cs = h * h * (double)(j - 1 - i);
-      nv += h * h;
-      n1 += cs * cs;
-      n2 += (cs + p.max_time_2_obs * h) * (cs + p.max_time_2_obs * h);
-    }
-    d.inrm_v[j - 1] = 1.0 / std::max(nv, floor_);
-    d.inrm_r1[j - 1] = 1.0 / std::max(n1, floor_);
-    d.inrm_r2[j - 1] = 1.0 / std::max(n2, floor_);
-  }
+  default_params(p);
   return MPCB_OK;
 }
 

@@ -10,8 +10,24 @@
 // linearise->QP loop instead of SLSQP, and an OSQP-style ADMM (sigma = 0, single-vector state, per-row
 // step-size ladder) for the QP.  Everything is fp64.
 #pragma once
-#include <cuda_runtime.h>
 #include <math.h>
+#ifdef __CUDACC__
+#include <cuda_runtime.h>
+#define MPCB_HD __host__ __device__ __forceinline__
+#define MPCB_D __device__ __forceinline__
+#else
+// host build: test infrastructure only (tests/hostbuild compiles these headers with g++ to validate the
+// algorithm on the CPU; the product library is nvcc-built and has no CPU path)
+#define MPCB_HD inline
+#define MPCB_D inline
+#define __host__
+#define __device__
+#endif
+#if defined(__CUDA_ARCH__)
+#define MPCB_LDG(p) __ldg(p)
+#else
+#define MPCB_LDG(p) (*(p))
+#endif
 
 namespace mpcb {
 
@@ -52,30 +68,37 @@ struct DevParams {
 // ------------------------------------------------------------------------------------------------
 // Reference-signal table.  searchsorted(side='left') clipped to [1, K-1], then the two-term formula.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ int seg_index(const double* __restrict__ s, int K, double x) {
+MPCB_HD int seg_index(const double* __restrict__ s, int K, double x) {
   int lo = 0, hi = K;
   while (lo < hi) {
     int mid = (lo + hi) >> 1;
-    if (__ldg(s + mid) < x) lo = mid + 1; else hi = mid;
+    if (MPCB_LDG(s + mid) < x) lo = mid + 1; else hi = mid;
   }
-  return min(max(lo, 1), K - 1);
+  return (lo < 1) ? 1 : ((lo > K - 1) ? K - 1 : lo);
 }
 
 // get_state(s)[1:5] and the slope of each column on the bracketing segment
-__device__ __forceinline__ void lookup_state(const DevTable& T, double s, double (&val)[4], double (&slope)[4]) {
+MPCB_HD void lookup_state(const DevTable& T, double s, double (&val)[4], double (&slope)[4]) {
   if (s >= T.s_max) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) { val[c] = T.last[c]; slope[c] = 0.0; }
     return;
   }
   const int i = seg_index(T.s, T.K, s);
-  const double x_lo = __ldg(T.s + i - 1), x_hi = __ldg(T.s + i);
+  const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double inv = 1.0 / (x_hi - x_lo);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
-  const double2* yl = reinterpret_cast<const double2*>(T.y + 4 * (i - 1));
-  const double2* yh = reinterpret_cast<const double2*>(T.y + 4 * i);
-  const double2 l0 = __ldg(yl), l1 = __ldg(yl + 1), h0 = __ldg(yh), h1 = __ldg(yh + 1);
-  const double ylo[4] = {l0.x, l0.y, l1.x, l1.y}, yhi[4] = {h0.x, h0.y, h1.x, h1.y};
+  double ylo[4], yhi[4];
+#if defined(__CUDA_ARCH__)
+  {
+    const double2* yl = reinterpret_cast<const double2*>(T.y + 4 * (i - 1));
+    const double2 l0 = __ldg(yl), l1 = __ldg(yl + 1), h0 = __ldg(yl + 2), h1 = __ldg(yl + 3);
+    ylo[0] = l0.x; ylo[1] = l0.y; ylo[2] = l1.x; ylo[3] = l1.y;
+    yhi[0] = h0.x; yhi[1] = h0.y; yhi[2] = h1.x; yhi[3] = h1.y;
+  }
+#else
+  for (int c = 0; c < 4; ++c) { ylo[c] = T.y[4 * (i - 1) + c]; yhi[c] = T.y[4 * i + c]; }
+#endif
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     val[c] = wl * yhi[c] + wr * ylo[c];
@@ -83,19 +106,19 @@ __device__ __forceinline__ void lookup_state(const DevTable& T, double s, double
   }
 }
 
-__device__ __forceinline__ void lookup_control(const DevTable& T, double s, double (&u)[2]) {
+MPCB_HD void lookup_control(const DevTable& T, double s, double (&u)[2]) {
   if (s >= T.s_max) { u[0] = 0.0; u[1] = 0.0; return; }
   const int i = seg_index(T.s, T.Ku, s);
-  const double x_lo = __ldg(T.s + i - 1), x_hi = __ldg(T.s + i);
+  const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
-  const double2 ul = __ldg(reinterpret_cast<const double2*>(T.u + 2 * (i - 1)));
-  const double2 uh = __ldg(reinterpret_cast<const double2*>(T.u + 2 * i));
-  u[0] = wl * uh.x + wr * ul.x;
-  u[1] = wl * uh.y + wr * ul.y;
+  const double ul0 = MPCB_LDG(T.u + 2 * (i - 1)), ul1 = MPCB_LDG(T.u + 2 * (i - 1) + 1);
+  const double uh0 = MPCB_LDG(T.u + 2 * i), uh1 = MPCB_LDG(T.u + 2 * i + 1);
+  u[0] = wl * uh0 + wr * ul0;
+  u[1] = wl * uh1 + wr * ul1;
 }
 
 // warm start, trajectory_tracking.py:223-246 (unclipped)
-__device__ __forceinline__ void warm_start(const DevTable& T, const DevParams& P, const double (&x0)[5],
+MPCB_HD void warm_start(const DevTable& T, const DevParams& P, const double (&x0)[5],
                                            const double (&obs)[2][2], int n_obs, double (&U)[NV]) {
   double s_cur = x0[0];
   const double v_cur = x0[4];
@@ -116,7 +139,7 @@ __device__ __forceinline__ void warm_start(const DevTable& T, const DevParams& P
 // ------------------------------------------------------------------------------------------------
 // Values-only rollout: X[6][5], cost, and constraint rows in the reference's order.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void rollout_values(const DevTable& T, const DevParams& P, const double (&x0)[5],
+MPCB_HD void rollout_values(const DevTable& T, const DevParams& P, const double (&x0)[5],
                                                const double (&U)[NV], double (&X)[NH + 1][5], double& cost) {
 #pragma unroll
   for (int c = 0; c < 5; ++c) X[0][c] = x0[c];
@@ -155,7 +178,7 @@ __device__ __forceinline__ void rollout_values(const DevTable& T, const DevParam
 
 // constraint rows of constraints_wrapper (trajectory_tracking.py:171-207) for step j (1-based), written to
 // out[0 .. 6+n_obs]; returns the number of rows.
-__device__ __forceinline__ int constraint_rows(const DevParams& P, const double (&Xj)[5], int j,
+MPCB_HD int constraint_rows(const DevParams& P, const double (&Xj)[5], int j,
                                                const double (&obs)[2][2], int n_obs, double* out) {
   const double s = Xj[0], d = Xj[1], o = Xj[2], v = Xj[4];
   int r = 0;

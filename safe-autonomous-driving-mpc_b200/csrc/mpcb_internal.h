@@ -1,0 +1,34 @@
+// mpcb_internal.h -- host-side context shared by the translation units of libmpcb200.so (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdio.h>
+
+#include "mpcb200.h"
+#include "mpcb_device.cuh"
+
+extern thread_local char g_cuda_err[512];
+int cuda_fail(cudaError_t e, const char* where);
+
+#define CK(call)                                        \
+  do {                                                  \
+    cudaError_t e_ = (call);                            \
+    if (e_ != cudaSuccess) return cuda_fail(e_, #call); \
+  } while (0)
+
+struct mpcb_ctx {
+  int device;
+  mpcb_params params;
+  mpcb::DevParams dp;
+  mpcb::DevTable dt;
+  int K, Ku;
+  double* d_s = nullptr;
+  double* d_y = nullptr;
+  double* d_u = nullptr;
+  // workspace for the host-buffer entry points
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  cudaStream_t stream = nullptr;   // private stream of the *_host entry points
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  bool timed = false;
+  unsigned long long launches = 0;
+};

@@ -1,0 +1,187 @@
+// mpcb_planner.cu -- kernels and C ABI of the planner function evaluator (see include/mpcb200.h, mpcb_planner.cuh).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include "mpcb200.h"
+#include "mpcb_internal.h"
+#include "mpcb_planner.cuh"
+
+namespace mpcb {
+
+constexpr int HS_THREADS = 64;                 // intervals per CTA
+constexpr int HS_STRIDE = 5 + 60 + 144;        // doubles staged per interval (odd-ish stride: conflict-free LDS/STS.64)
+
+// One thread per collocation interval (chunk c, interval k).  Results are staged per thread in shared memory and
+// written out by the whole CTA so that every global store instruction covers contiguous addresses.
+template <bool WANT_JAC, bool WANT_HESS>
+__global__ void __launch_bounds__(HS_THREADS)
+mpcb_hs_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ PlanParams P, int n_int, int N,
+                    const double* __restrict__ z, const double* __restrict__ lam, double* __restrict__ defect,
+                    double* __restrict__ jac, double* __restrict__ hess) {
+  extern __shared__ double stage[];
+  const int t = threadIdx.x;
+  const int first = blockIdx.x * HS_THREADS;
+  const int i = first + t;
+  const int nb = min(HS_THREADS, n_int - first);
+  double* my = stage + (size_t)t * HS_STRIDE;
+  if (i < n_int) {
+    const int c = i / N, k = i - c * N;
+    const double* zc = z + (size_t)c * (8 * N + 5);
+    double xk[5], xn[5], u[2];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) { xk[q] = zc[5 * k + q]; xn[q] = zc[5 * (k + 1) + q]; }
+    u[0] = zc[5 * (N + 1) + 2 * k];
+    u[1] = zc[5 * (N + 1) + 2 * k + 1];
+    hs_interval<WANT_JAC, WANT_HESS>(T, P, xk, xn, u, WANT_HESS ? lam + (size_t)i * 5 : nullptr, my, my + 5, my + 65);
+  }
+  __syncthreads();
+  for (int e = t; e < nb * 5; e += HS_THREADS) defect[(size_t)first * 5 + e] = stage[(e / 5) * HS_STRIDE + e % 5];
+  if (WANT_JAC && jac)
+    for (int e = t; e < nb * 60; e += HS_THREADS) jac[(size_t)first * 60 + e] = stage[(e / 60) * HS_STRIDE + 5 + e % 60];
+  if (WANT_HESS && hess)
+    for (int e = t; e < nb * 144; e += HS_THREADS)
+      hess[(size_t)first * 144 + e] = stage[(e / 144) * HS_STRIDE + 65 + e % 144];
+}
+
+// One thread per node (chunk c, node k = 0..N): inequality rows, stage cost and its gradient in z layout.
+__global__ void __launch_bounds__(128)
+mpcb_hs_nodes_kernel(const __grid_constant__ PlanParams P, int n_nodes, int N, const double* __restrict__ z,
+                     const double* __restrict__ s0, const double* __restrict__ vmin_nodes,
+                     const double* __restrict__ vmax_nodes, double* __restrict__ node_rows,
+                     double* __restrict__ ctrl_rows, double* __restrict__ cost_terms, double* __restrict__ cost_grad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  const int c = i / (N + 1), k = i - c * (N + 1);
+  const int nz = 8 * N + 5;
+  const double* zc = z + (size_t)c * nz;
+  double x[5];
+#pragma unroll
+  for (int q = 0; q < 5; ++q) x[q] = zc[5 * k + q];
+  const bool inner = k < N;
+  const double slack = inner ? zc[7 * N + 5 + k] : 0.0;                      // no slack on the final state (:256-259)
+  const double vmin = vmin_nodes ? vmin_nodes[i] : P.v_min_c;
+  const double vmax = vmax_nodes ? vmax_nodes[i] : P.v_max_c;
+  if (node_rows) {
+    double r[6];
+    hs_node_rows(P, x, slack, vmin, vmax, r);
+#pragma unroll
+    for (int q = 0; q < 6; ++q) node_rows[(size_t)i * 6 + q] = r[q];
+  }
+  double g[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (inner) {
+    const double u[2] = {zc[5 * (N + 1) + 2 * k], zc[5 * (N + 1) + 2 * k + 1]};
+    if (ctrl_rows) {
+      double r[5];
+      hs_ctrl_rows(P, u, slack, r);
+#pragma unroll
+      for (int q = 0; q < 5; ++q) ctrl_rows[((size_t)c * N + k) * 5 + q] = r[q];
+    }
+    const double ct = hs_stage_cost(P, x, u, slack, s0[c], g);
+    if (cost_terms) cost_terms[(size_t)c * N + k] = ct;
+  }
+  if (cost_grad) {
+    double* gc = cost_grad + (size_t)c * nz;
+    gc[5 * k + 0] = g[0]; gc[5 * k + 1] = g[1]; gc[5 * k + 2] = g[2]; gc[5 * k + 3] = 0.0; gc[5 * k + 4] = 0.0;
+    if (inner) {
+      gc[5 * (N + 1) + 2 * k] = g[3];
+      gc[5 * (N + 1) + 2 * k + 1] = g[4];
+      gc[7 * N + 5 + k] = g[5];
+    }
+  }
+}
+
+// cost = sum_k terms in the reference's order (sequential accumulation, :141-169), one thread per chunk
+__global__ void mpcb_hs_cost_sum_kernel(int C, int N, const double* __restrict__ terms, double* __restrict__ cost) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  double acc = 0.0;
+  for (int k = 0; k < N; ++k) acc += terms[(size_t)c * N + k];
+  cost[c] = acc;
+}
+
+}  // namespace mpcb
+
+using namespace mpcb;
+
+static int derive_plan(const mpcb_planner_params* p, PlanParams& d) {
+  if (!p || !(p->dt > 0) || (p->simpson_sign != 1 && p->simpson_sign != -1)) return MPCB_ERR_INVALID;
+  d.dt = p->dt;
+  d.w_y = p->w_y; d.w_s = p->w_s; d.w_u = p->w_u; d.w_slack = p->w_slack;
+  for (int i = 0; i < 2; ++i) { d.u_min[i] = p->u_min[i]; d.u_max[i] = p->u_max[i]; }
+  d.k_min = p->k_min; d.k_max = p->k_max; d.a_max = p->a_max;
+  d.sigma = (double)p->simpson_sign;
+  d.v_min_c = p->v_min; d.v_max_c = p->v_max;
+  d.s_total = p->s_total;
+  return MPCB_OK;
+}
+
+extern "C" {
+
+int mpcb_planner_default_params(mpcb_planner_params* p) {
+  if (!p) return MPCB_ERR_INVALID;
+  memset(p, 0, sizeof(*p));
+  p->dt = 0.3;                                               // trajectory_planning.py:514
+  p->w_y = 10.0; p->w_s = 10.0; p->w_u = 0.1; p->w_slack = 100.0;   // :14
+  p->u_min[0] = -0.6; p->u_min[1] = -5.0; p->u_max[0] = 0.6; p->u_max[1] = 4.0;   // :36-37
+  p->k_min = -0.8; p->k_max = 0.8;                           // :44-45
+  p->a_max = 6.0;                                            // :48
+  p->simpson_sign = -1;                                      // as committed (:198)
+  p->v_min = 0.0; p->v_max = 1.0;                            // :476-477 / :465 (v_max_array default)
+  p->s_total = 0.0;
+  return MPCB_OK;
+}
+
+int mpcb_hs_eval(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int N, const double* z, const double* lam,
+                 double* defect, double* jac, double* hess, void* cuda_stream) {
+  if (!h || n_chunks < 0 || N < 1 || (n_chunks > 0 && (!z || !defect)) || (hess && !lam)) return MPCB_ERR_INVALID;
+  PlanParams d;
+  int rc = derive_plan(p, d);
+  if (rc != MPCB_OK) return rc;
+  if (n_chunks == 0) return MPCB_OK;
+  const long long n_int_ll = (long long)n_chunks * N;
+  if (n_int_ll > 0x7fffffffLL / 144) return MPCB_ERR_INVALID;
+  const int n_int = (int)n_int_ll;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int grid = (n_int + HS_THREADS - 1) / HS_THREADS;
+  const size_t smem = sizeof(double) * HS_THREADS * HS_STRIDE;
+  auto launch = [&](auto kern) -> int {
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
+    kern<<<grid, HS_THREADS, smem, st>>>(h->dt, d, n_int, N, z, lam, defect, jac, hess);
+    return MPCB_OK;
+  };
+  if (hess) rc = launch(mpcb_hs_eval_kernel<true, true>);       // hess implies the Jacobian intermediates
+  else if (jac) rc = launch(mpcb_hs_eval_kernel<true, false>);
+  else rc = launch(mpcb_hs_eval_kernel<false, false>);
+  if (rc != MPCB_OK) return rc;
+  CK(cudaGetLastError());
+  h->launches++;
+  return MPCB_OK;
+}
+
+int mpcb_hs_nodes(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int N, const double* z, const double* s0,
+                  const double* vmin_nodes, const double* vmax_nodes, double* node_rows, double* ctrl_rows,
+                  double* cost_terms, double* cost, double* cost_grad, void* cuda_stream) {
+  if (!h || n_chunks < 0 || N < 1 || (n_chunks > 0 && (!z || !s0)) || (cost && !cost_terms)) return MPCB_ERR_INVALID;
+  PlanParams d;
+  int rc = derive_plan(p, d);
+  if (rc != MPCB_OK) return rc;
+  if (n_chunks == 0) return MPCB_OK;
+  const long long nn = (long long)n_chunks * (N + 1);
+  if (nn > 0x7fffffffLL / 8) return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  mpcb_hs_nodes_kernel<<<(int)((nn + 127) / 128), 128, 0, st>>>(d, (int)nn, N, z, s0, vmin_nodes, vmax_nodes, node_rows,
+                                                                ctrl_rows, cost_terms, cost_grad);
+  CK(cudaGetLastError());
+  h->launches++;
+  if (cost) {
+    mpcb_hs_cost_sum_kernel<<<(n_chunks + 127) / 128, 128, 0, st>>>(n_chunks, N, cost_terms, cost);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
+  return MPCB_OK;
+}
+
+}  // extern "C"
