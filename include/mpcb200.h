@@ -60,6 +60,15 @@ typedef struct mpcb_params {
   double eps_infeas;               /* infeasibility-certificate tolerance, default 1e-4 */
   double step_tol;                 /* SQP termination on |dU|_inf, default 1e-7 */
   double feas_tol;                 /* constraint tolerance for flags / active set, default 1e-6 */
+  /* two-pass scheme: a first pass with two-level step sizes (inactive rows ~0, active rows a large augmented-
+   * Lagrangian weight: a primal-dual active-set iteration run on the ADMM machinery) solves the non-degenerate
+   * problems in a few iterations; whatever it does not certify as solved is re-solved from scratch by the robust
+   * ladder pass above.  fast_pass = 0 disables the first pass. */
+  int fast_pass;                   /* default 1 */
+  double fast_rho_off, fast_rho_on;/* defaults 1e-9, 1e6 */
+  int fast_max_rounds;             /* default 6 */
+  int fast_max_segments;           /* default 4 */
+  int fast_segment_iters;          /* default 2 */
 } mpcb_params;
 
 typedef struct mpcb_ctx* mpcb_handle;
@@ -129,6 +138,9 @@ int mpcb_memcpy_d2h(mpcb_handle h, void* dst, const void* src, unsigned long lon
 /* Device time in milliseconds of the kernel launched by the last mpcb_solve_batch* call on this handle
  * (CUDA events on the launching stream; synchronises that stream). */
 int mpcb_last_kernel_ms(mpcb_handle h, float* ms);
+/* Device time of the two passes of the last solve (first: two-level pass incl. the list reset; second: robust pass over
+ * the problems the first did not certify) and how many problems the second pass handled. */
+int mpcb_last_pass_ms(mpcb_handle h, float* first_ms, float* second_ms, int* n_second);
 /* Number of kernels this library has launched on this handle since creation. */
 unsigned long long mpcb_launch_count(mpcb_handle h);
 

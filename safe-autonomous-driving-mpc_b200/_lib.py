@@ -31,6 +31,8 @@ class Params(C.Structure):
         ("alpha", C.c_double),
         ("eps_prim", C.c_double), ("eps_dual", C.c_double), ("eps_infeas", C.c_double),
         ("step_tol", C.c_double), ("feas_tol", C.c_double),
+        ("fast_pass", C.c_int), ("fast_rho_off", C.c_double), ("fast_rho_on", C.c_double),
+        ("fast_max_rounds", C.c_int), ("fast_max_segments", C.c_int), ("fast_segment_iters", C.c_int),
     ]
 
 
@@ -69,6 +71,7 @@ SYMBOLS = {
     "mpcb_memcpy_h2d": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong]),
     "mpcb_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong]),
     "mpcb_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
+    "mpcb_last_pass_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
     "mpcb_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "mpcb_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "mpcb_planner_default_params": (C.c_int, [C.POINTER(PlannerParams)]),

@@ -15,20 +15,28 @@
 
 namespace mpcb {
 
-constexpr int SOLVE_THREADS = 64;   // problems per CTA
+constexpr int SOLVE_THREADS = 128;  // problems per CTA; 255 registers/thread -> 2 CTAs per SM
 constexpr int EVAL_THREADS = 128;
 
 // ------------------------------------------------------------------------------------------------
-// Solve kernel: one thread per problem.
+// Solve kernel: one thread per problem, CTA-uniform loop control.
+//   work list   idx == nullptr: problems 0..B-1;  else problems idx[0 .. *n_idx - 1] (second pass)
+//   FIRST_PASS  problems this pass cannot certify (iteration caps hit, or a verdict only the robust pass may give)
+//               are appended to fb_list / fb_count instead of being written out.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SOLVE_THREADS)
+template <bool FIRST_PASS>
+__global__ void __launch_bounds__(SOLVE_THREADS, 2)
 mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
+                  const int* __restrict__ idx, const int* __restrict__ n_idx,
                   const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
                   double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
                   int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
-                  unsigned long long* __restrict__ active_out) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = b < B;
+                  unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  const int n_work = idx ? min(*n_idx, B) : B;
+  if ((int)(blockIdx.x * blockDim.x) >= n_work) return;          // CTA-uniform
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < n_work;
+  const int b = live ? (idx ? idx[t] : t) : 0;
   Problem pb;
   if (live) {
 #pragma unroll
@@ -44,6 +52,11 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
   }
   SolveOut so = solve_one(T, P, pb, live);
   if (!live) return;
+  if (FIRST_PASS && so.status == MPCB_MAXITER) {                   // not certified: leave it to the robust pass
+    fb_list[atomicAdd(fb_count, 1)] = b;
+    if (iters_out) { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
+    return;
+  }
 
   // final evaluation at U*: predict, cost, constraint rows in the reference's order
   double X[NH + 1][5];
@@ -66,7 +79,14 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
   for (int i = 0; i < NV; ++i)
     if (pb.U[i] - P.umin[i & 1] <= P.feas_tol || P.umax[i & 1] - pb.U[i] <= P.feas_tol) act |= (1ull << (45 + i));
   int status = so.status;
-  if (cmin < -P.feas_tol) status = MPCB_INFEASIBLE;
+  if (cmin < -P.feas_tol) {
+    if (FIRST_PASS && !so.const_infeasible) {                      // a violated row the first pass cannot explain
+      fb_list[atomicAdd(fb_count, 1)] = b;
+      if (iters_out) { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
+      return;
+    }
+    status = MPCB_INFEASIBLE;
+  }
 
 #pragma unroll
   for (int i = 0; i < NV; ++i) U_out[(size_t)b * NV + i] = pb.U[i];
@@ -78,7 +98,10 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
   }
   if (obj_out) obj_out[b] = cost;
   if (status_out) status_out[b] = status;
-  if (iters_out) { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
+  if (iters_out) {
+    if (idx) { iters_out[2 * b] += so.rounds; iters_out[2 * b + 1] += so.iters; }     // work of both passes
+    else { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
+  }
   if (cmin_out) cmin_out[b] = cmin;
   if (active_out) active_out[b] = act;
 }
@@ -283,8 +306,10 @@ int mpcb_table_knots(mpcb_table_handle t) { return t ? t->K : MPCB_ERR_INVALID; 
 int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int device) {
   if (!out || !p || !t) return MPCB_ERR_INVALID;
   *out = nullptr;
-  DevParams dp;
-  int rc = derive_params(*p, dp);
+  DevParams dp, dp_fast;
+  int rc = derive_params(*p, dp, false);
+  if (rc != MPCB_OK) return rc;
+  rc = derive_params(*p, dp_fast, true);
   if (rc != MPCB_OK) return rc;
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -302,6 +327,7 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   c->device = device;
   c->params = *p;
   c->dp = dp;
+  c->dp_fast = dp_fast;
   const int K = t->K;
   c->K = K;
   c->Ku = t->Ku;
@@ -316,6 +342,7 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate"));
   if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
+  if ((e = cudaEventCreate(&c->ev_mid)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   c->dt.s = c->d_s; c->dt.y = c->d_y; c->dt.u = c->d_u;
   c->dt.K = K; c->dt.Ku = c->Ku; c->dt.s_max = t->s_max;
   for (int k = 0; k < 4; ++k) c->dt.last[k] = t->last_row[1 + k];
@@ -330,8 +357,10 @@ int mpcb_destroy(mpcb_handle h) {
   if (h->d_y) cudaFree(h->d_y);
   if (h->d_u) cudaFree(h->d_u);
   if (h->ws) cudaFree(h->ws);
+  if (h->fb) cudaFree(h->fb);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_mid) cudaEventDestroy(h->ev_mid);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MPCB_OK;
@@ -342,13 +371,37 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
                         double* Xpred_out, double* obj_out, int* status_out, int* iters_out, double* cmin_out,
                         unsigned long long* active_out, cudaStream_t st) {
   const int grid = (B + SOLVE_THREADS - 1) / SOLVE_THREADS;
+  if (h->params.fast_pass && B > h->fb_cap) {        // fallback list: [count, idx[B]]
+    if (h->fb) { CK(cudaFree(h->fb)); h->fb = nullptr; h->fb_cap = 0; }
+    if (cudaMalloc(&h->fb, sizeof(int) * ((size_t)B + 1)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
+    h->fb_cap = B;
+  }
   CK(cudaEventRecord(h->ev0, st));
-  mpcb_solve_kernel<<<grid, SOLVE_THREADS, 0, st>>>(h->dt, h->dp, B, x0, obs_sv, n_obs, U_out, Xpred_out, obj_out,
-                                                   status_out, iters_out, cmin_out, active_out);
-  CK(cudaGetLastError());
+  if (h->params.fast_pass) {
+    int* fb_count = h->fb;
+    int* fb_list = h->fb + 1;
+    CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
+    mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, 0, st>>>(h->dt, h->dp_fast, B, nullptr, nullptr, x0, obs_sv, n_obs,
+                                                           U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
+                                                           active_out, fb_list, fb_count);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(h->ev_mid, st));
+    // second pass over whatever the first did not certify; CTAs beyond the list length exit at once
+    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, 0, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs,
+                                                            U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
+                                                            active_out, nullptr, nullptr);
+    CK(cudaGetLastError());
+    h->launches += 2;
+  } else {
+    CK(cudaEventRecord(h->ev_mid, st));
+    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, 0, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
+                                                            U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
+                                                            active_out, nullptr, nullptr);
+    CK(cudaGetLastError());
+    h->launches++;
+  }
   CK(cudaEventRecord(h->ev1, st));
   h->timed = true;
-  h->launches++;
   return MPCB_OK;
 }
 
@@ -453,6 +506,22 @@ int mpcb_last_kernel_ms(mpcb_handle h, float* ms) {
   CK(cudaSetDevice(h->device));
   CK(cudaEventSynchronize(h->ev1));
   CK(cudaEventElapsedTime(ms, h->ev0, h->ev1));
+  return MPCB_OK;
+}
+
+int mpcb_last_pass_ms(mpcb_handle h, float* first_ms, float* second_ms, int* n_second) {
+  if (!h || !h->timed) return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  CK(cudaEventSynchronize(h->ev1));
+  float a = 0.f, b = 0.f;
+  CK(cudaEventElapsedTime(&a, h->ev0, h->ev_mid));
+  CK(cudaEventElapsedTime(&b, h->ev_mid, h->ev1));
+  if (first_ms) *first_ms = a;
+  if (second_ms) *second_ms = b;
+  if (n_second) {
+    *n_second = 0;
+    if (h->params.fast_pass && h->fb) CK(cudaMemcpy(n_second, h->fb, sizeof(int), cudaMemcpyDeviceToHost));
+  }
   return MPCB_OK;
 }
 

@@ -57,7 +57,7 @@ struct DevParams {
   double alpha_lane[3];// 0, wheelbase/2, wheelbase
   double brake_lookahead, brake_guess;
   int max_rounds, max_segments, segment_iters;
-  int n_rung, e_init;
+  int n_rung, e_init, hysteresis, drop_all, up_step, trust_cert;
   double lad[MAXRUNG]; // step-size ladder rho_lo * fac^k (capped at rho_hi)
   double lad_ratio[MAXRUNG]; // lad[k-1]/lad[k] (k>=1): rescale of (v - z) when a row moves up one rung
   double relax;        // ADMM over-relaxation alpha

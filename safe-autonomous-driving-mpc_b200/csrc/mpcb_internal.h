@@ -18,7 +18,8 @@ int cuda_fail(cudaError_t e, const char* where);
 struct mpcb_ctx {
   int device;
   mpcb_params params;
-  mpcb::DevParams dp;
+  mpcb::DevParams dp;        // robust (ladder) pass
+  mpcb::DevParams dp_fast;   // first pass
   mpcb::DevTable dt;
   int K, Ku;
   double* d_s = nullptr;
@@ -27,8 +28,10 @@ struct mpcb_ctx {
   // workspace for the host-buffer entry points
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  int* fb = nullptr;          // [1 + fb_cap]: count, then indices of problems left to the second pass
+  int fb_cap = 0;
   cudaStream_t stream = nullptr;   // private stream of the *_host entry points
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
   bool timed = false;
   unsigned long long launches = 0;
 };

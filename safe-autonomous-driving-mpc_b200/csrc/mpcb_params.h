@@ -2,6 +2,7 @@
 // libmpcb200.so and by the g++ test build of the device headers (tests/hostbuild).
 #pragma once
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -25,9 +26,15 @@ inline void default_params(mpcb_params* p) {
   p->alpha = 1.6;
   p->eps_prim = 1e-9; p->eps_dual = 1e-8; p->eps_infeas = 1e-4;
   p->step_tol = 1e-7; p->feas_tol = 1e-6;
+  p->fast_pass = 1;
+  p->fast_rho_off = 1e-9; p->fast_rho_on = 1e6;
+  p->fast_max_rounds = 6; p->fast_max_segments = 4; p->fast_segment_iters = 2;
 }
 
-inline int derive_params(const mpcb_params& p, DevParams& d) {
+// fast = true: constants of the first pass (two-level step sizes: "off" ~ 0 for inactive rows, "on" = a large
+// augmented-Lagrangian weight for active rows, alpha = 1, no infeasibility verdicts); fast = false: the robust
+// ladder policy of the second pass.
+inline int derive_params(const mpcb_params& p, DevParams& d, bool fast = false) {
   if (p.N != NH) return MPCB_ERR_UNSUPPORTED;
   if (!(p.dt > 0) || p.max_rounds < 1 || p.max_segments < 1 || p.segment_iters < 1) return MPCB_ERR_INVALID;
   if (!(p.rho_lo > 0) || !(p.rho_hi >= p.rho_lo) || !(p.alpha > 0 && p.alpha < 2)) return MPCB_ERR_INVALID;
@@ -40,7 +47,12 @@ inline int derive_params(const mpcb_params& p, DevParams& d) {
   d.alpha_lane[0] = 0.0; d.alpha_lane[1] = p.wheelbase / 2.0; d.alpha_lane[2] = p.wheelbase;
   d.brake_lookahead = p.brake_lookahead; d.brake_guess = p.brake_guess;
   d.max_rounds = p.max_rounds; d.max_segments = p.max_segments; d.segment_iters = p.segment_iters;
-  const double fac = 10.0;
+  double fac = 10.0;
+  d.hysteresis = 1;
+#ifndef __CUDACC__
+  if (getenv("MPCB_FAC")) fac = atof(getenv("MPCB_FAC"));
+  if (getenv("MPCB_HYST")) d.hysteresis = atoi(getenv("MPCB_HYST"));
+#endif
   int n = 0;
   double r = p.rho_lo;
   while (n < MAXRUNG) {
@@ -55,7 +67,34 @@ inline int derive_params(const mpcb_params& p, DevParams& d) {
   for (int k = 0; k < n; ++k)
     if (fabs(log(d.lad[k] / p.rho_init)) < fabs(log(d.lad[best] / p.rho_init))) best = k;
   d.e_init = best;
+#ifndef __CUDACC__
+  if (getenv("MPCB_LAD")) {
+    const char* q = getenv("MPCB_LAD");
+    n = 0;
+    while (*q && n < MAXRUNG) { char* e; d.lad[n++] = strtod(q, &e); q = (*e == ',') ? e + 1 : e; }
+    d.n_rung = n;
+    d.lad_ratio[0] = 1.0;
+    for (int k = 1; k < n; ++k) d.lad_ratio[k] = d.lad[k - 1] / d.lad[k];
+    d.e_init = getenv("MPCB_EINIT") ? atoi(getenv("MPCB_EINIT")) : 1;
+  }
+  d.drop_all = getenv("MPCB_DROP") ? atoi(getenv("MPCB_DROP")) : 0;
+  d.up_step = getenv("MPCB_UP") ? atoi(getenv("MPCB_UP")) : 1;
+#else
+  d.drop_all = 0; d.up_step = 1;
+#endif
   d.relax = p.alpha;
+  d.trust_cert = 1;
+  if (fast) {
+    if (!(p.fast_rho_off > 0) || !(p.fast_rho_on > p.fast_rho_off) || p.fast_max_rounds < 1 ||
+        p.fast_max_segments < 1 || p.fast_segment_iters < 1)
+      return MPCB_ERR_INVALID;
+    d.lad[0] = p.fast_rho_off; d.lad[1] = p.fast_rho_on;
+    d.lad_ratio[0] = 1.0; d.lad_ratio[1] = d.lad[0] / d.lad[1];
+    d.n_rung = 2; d.e_init = 0; d.hysteresis = 0; d.drop_all = 1; d.up_step = 1;
+    d.relax = 1.0;
+    d.trust_cert = 0;
+    d.max_rounds = p.fast_max_rounds; d.max_segments = p.fast_max_segments; d.segment_iters = p.fast_segment_iters;
+  }
   d.eps_p = p.eps_prim; d.eps_d = p.eps_dual; d.eps_inf = p.eps_infeas;
   d.step_tol = p.step_tol; d.feas_tol = p.feas_tol;
   const double h = p.dt, floor_ = NRM2_FLOOR;

@@ -19,6 +19,14 @@
 #include "mpcb200.h"
 #include "mpcb_device.cuh"
 
+// Loop control is uniform over the whole CTA (all threads reach every barrier): the CTA walks through the
+// straight-line solver code together, so one instruction stream per CTA goes through the instruction caches.
+#if defined(__CUDA_ARCH__)
+#define MPCB_ALL(pred) (__syncthreads_and(pred) != 0)
+#else
+#define MPCB_ALL(pred) (pred)
+#endif
+
 namespace mpcb {
 
 constexpr int M_LANE = 12;
@@ -504,11 +512,12 @@ __device__ __forceinline__ void admm_iter(const DevParams& P, Problem& pb, SegSt
       const bool a_now = (vn < lo) || (vn > hi);
       const bool a_prev = (pb.act_prev >> r) & 1ull;
       double vnew = vn;
-      if (a_now && a_prev && e < P.n_rung - 1) {
-        pb.E.set(r, e + 1);
-        vnew = fma(P.lad_ratio[e + 1], vn - zn, zn);   // keep (z, y): v' = z + (rho/rho') (v - z)
-      } else if (!a_now && !a_prev && e > 0) {
-        pb.E.set(r, e - 1);                            // inactive: v == z, nothing to rescale
+      if (a_now && (a_prev || !P.hysteresis) && e < P.n_rung - 1) {
+        const int e2 = (e + P.up_step < P.n_rung - 1) ? e + P.up_step : P.n_rung - 1;
+        pb.E.set(r, e2);
+        vnew = fma(P.lad[e] / P.lad[e2], vn - zn, zn);   // keep (z, y): v' = z + (rho/rho') (v - z)
+      } else if (!a_now && (!a_prev || !P.hysteresis) && e > 0) {
+        pb.E.set(r, P.drop_all ? 0 : e - 1);           // inactive: v == z, nothing to rescale
       }
       if (a_now) act |= (1ull << r);
       v = vnew;
@@ -529,7 +538,7 @@ __device__ __forceinline__ void admm_iter(const DevParams& P, Problem& pb, SegSt
 // ------------------------------------------------------------------------------------------------
 // Whole solve for one problem.  Warp-uniform loops (votes) so that divergence only idles lanes.
 // ------------------------------------------------------------------------------------------------
-struct SolveOut { int status, rounds, iters; };
+struct SolveOut { int status, rounds, iters; bool const_infeasible; };
 
 __device__ __forceinline__ void init_admm_state(const DevParams& P, Problem& pb) {
   // z = clip(A U), y = 0  ->  v = z ; all rows on the initial rung
@@ -542,7 +551,6 @@ __device__ __forceinline__ void init_admm_state(const DevParams& P, Problem& pb)
 }
 
 __device__ __forceinline__ SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, bool live) {
-  const unsigned full = 0xffffffffu;
   // obstacle row offsets
 #pragma unroll
   for (int k = 0; k < 2; ++k)
@@ -553,31 +561,40 @@ __device__ __forceinline__ SolveOut solve_one(const DevTable& T, const DevParams
 #pragma unroll
   for (int i = 0; i < NV; ++i) pb.U[i] = clipd(pb.U[i], P.umin[i & 1], P.umax[i & 1]);  // scipy clips x0 to the bounds
 
-  SolveOut out{MPCB_MAXITER, 0, 0};
+  SolveOut out{MPCB_MAXITER, 0, 0, false};
   bool done = !live;
   bool infeasible = false;
   bool first = true;
   for (int round = 0; round < P.max_rounds; ++round) {
-    if (__all_sync(full, done)) break;
+    if (MPCB_ALL(done)) break;
     if (!done) {
       double cviol;
       linearise(T, P, pb, cviol);
       if (first) { init_admm_state(P, pb); first = false; }
-      if (cviol > P.feas_tol) infeasible = true;
+      if (cviol > P.feas_tol) { infeasible = true; out.const_infeasible = true; }
       out.rounds++;
     }
     bool conv = done;
     bool cert = false;
     for (int seg = 0; seg < P.max_segments; ++seg) {
-      if (__all_sync(full, conv)) break;
+      if (MPCB_ALL(conv)) break;
       if (!conv) {
         factor(P, pb);
         SegStats st;
         for (int it = 0; it < P.segment_iters - 1; ++it) admm_iter<false>(P, pb, st);
         admm_iter<true>(P, pb, st);
         out.iters += P.segment_iters;
+#ifdef MPCB_TRACE
+        if (getenv("MPCB_TRACE")) {
+          printf("  r%d s%d rp %.2e rd %.2e nd %.2e act %012llx E", round, seg, st.rp, st.rd, st.nd, pb.act_prev);
+          for (int r = 0; r < M_ROWS; ++r) printf("%d", pb.E.get(r));
+          printf(" x");
+          for (int i = 0; i < NV; ++i) printf(" %.4f", pb.x[i]);
+          printf("\n");
+        }
+#endif
         if (st.rp <= P.eps_p && st.rd <= P.eps_d) conv = true;
-        else if (st.nd > 1e-9 && st.atdy <= P.eps_inf * st.nd && st.sup < -P.eps_inf * st.nd &&
+        else if (P.trust_cert && st.nd > 1e-9 && st.atdy <= P.eps_inf * st.nd && st.sup < -P.eps_inf * st.nd &&
                  st.bad <= P.eps_inf * st.nd) { conv = true; cert = true; }
       }
     }
@@ -587,6 +604,7 @@ __device__ __forceinline__ SolveOut solve_one(const DevTable& T, const DevParams
       for (int i = 0; i < NV; ++i) { step = fmax(step, fabs(pb.x[i] - pb.U[i])); pb.U[i] = pb.x[i]; }
       if (cert) { infeasible = true; done = true; }
       else if (conv && step < P.step_tol) { done = true; out.status = 0; }
+      else if (!conv && !P.trust_cert) done = true;   // first pass: a QP it cannot close goes to the robust pass
     }
   }
   if (infeasible) out.status = 2;

@@ -253,6 +253,12 @@ class BatchedTracker:
         check(self._lib.mpcb_last_kernel_ms(self._need(), C.byref(ms)))
         return ms.value
 
+    def last_pass_ms(self):
+        """(first-pass ms, second-pass ms, problems handled by the second pass) of the last solve."""
+        a, b, n = C.c_float(), C.c_float(), C.c_int()
+        check(self._lib.mpcb_last_pass_ms(self._need(), C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
+
     def launch_count(self):
         return int(self._lib.mpcb_launch_count(self._need()))
 

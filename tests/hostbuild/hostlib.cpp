@@ -2,6 +2,8 @@
 // algorithms (planner derivative formulas, tracking solver) can be validated on the CPU against the oracle
 // before / without a GPU.  Nothing in the product package loads this library; the product has no CPU path.
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -58,38 +60,53 @@ int host_hs_eval(const double* s, const double* y, int K, double dt, int simpson
 
 extern "C" {
 
-// The tracking solver (solve_one, the code mpcb_solve_kernel runs per thread) on the CPU, one problem at a time.
-// `p` may be null (defaults).  Outputs like mpcb_solve_batch.
+// The tracking solver (solve_one, the code mpcb_solve_kernel runs per thread) on the CPU, one problem at a time,
+// with the same two-pass logic as launch_solve.  `p` may be null (defaults).  Outputs like mpcb_solve_batch;
+// pass_out[b] = 1 when the first pass certified the problem, 2 when the robust pass produced the answer.
 int host_solve_batch(const double* s, const double* y, const double* u, int K, int Ku, double s_max,
                      const double* last4, const mpcb_params* p, int B, const double* x0, const double* obs_sv,
-                     const int* n_obs, double* U_out, int* status_out, int* iters_out, double* obj_out) {
+                     const int* n_obs, double* U_out, int* status_out, int* iters_out, double* obj_out,
+                     int* pass_out) {
   DevTable T = make_table(s, y, u, K, Ku, s_max, last4);
   mpcb_params pp;
   if (p) pp = *p; else default_params(&pp);
-  DevParams P;
-  int rc = derive_params(pp, P);
+  DevParams Pr, Pf;
+  int rc = derive_params(pp, Pr, false);
+  if (rc != 0) return rc;
+  rc = derive_params(pp, Pf, true);
   if (rc != 0) return rc;
   for (int b = 0; b < B; ++b) {
-    Problem pb;
-    for (int c = 0; c < 5; ++c) pb.x0[c] = x0[5 * b + c];
-    for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[4 * b + 2 * k]; pb.obs[k][1] = obs_sv[4 * b + 2 * k + 1]; }
-    pb.n_obs = std::min(std::max(n_obs[b], 0), 2);
-    SolveOut so = solve_one(T, P, pb, true);
-    double X[NH + 1][5];
-    double cost;
-    rollout_values(T, P, pb.x0, pb.U, X, cost);
-    double cmin = BIG;
-    for (int j = 1; j <= NH; ++j) {
-      double rows[9];
-      const int nr = constraint_rows(P, X[j], j, pb.obs, pb.n_obs, rows);
-      for (int r = 0; r < nr; ++r) cmin = fmin(cmin, rows[r]);
+    int rounds = 0, iters = 0;
+    for (int pass = pp.fast_pass ? 1 : 2; pass <= 2; ++pass) {
+      const DevParams& P = (pass == 1) ? Pf : Pr;
+      Problem pb;
+      for (int c = 0; c < 5; ++c) pb.x0[c] = x0[5 * b + c];
+      for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[4 * b + 2 * k]; pb.obs[k][1] = obs_sv[4 * b + 2 * k + 1]; }
+      pb.n_obs = std::min(std::max(n_obs[b], 0), 2);
+      SolveOut so = solve_one(T, P, pb, true);
+      rounds += so.rounds; iters += so.iters;
+      if (pass == 1 && so.status == MPCB_MAXITER) continue;
+      double X[NH + 1][5];
+      double cost;
+      rollout_values(T, P, pb.x0, pb.U, X, cost);
+      double cmin = BIG;
+      for (int j = 1; j <= NH; ++j) {
+        double rows[9];
+        const int nr = constraint_rows(P, X[j], j, pb.obs, pb.n_obs, rows);
+        for (int r = 0; r < nr; ++r) cmin = fmin(cmin, rows[r]);
+      }
+      int status = so.status;
+      if (cmin < -P.feas_tol) {
+        if (pass == 1 && !so.const_infeasible) continue;
+        status = MPCB_INFEASIBLE;
+      }
+      for (int i = 0; i < NV; ++i) U_out[10 * b + i] = pb.U[i];
+      if (status_out) status_out[b] = status;
+      if (iters_out) { iters_out[2 * b] = rounds; iters_out[2 * b + 1] = iters; }
+      if (obj_out) obj_out[b] = cost;
+      if (pass_out) pass_out[b] = pass;
+      break;
     }
-    int status = so.status;
-    if (cmin < -P.feas_tol) status = MPCB_INFEASIBLE;
-    for (int i = 0; i < NV; ++i) U_out[10 * b + i] = pb.U[i];
-    if (status_out) status_out[b] = status;
-    if (iters_out) { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
-    if (obj_out) obj_out[b] = cost;
   }
   return 0;
 }

@@ -37,7 +37,7 @@ def main():
     x0, obs, n = P.monte_carlo_problems(tab, 65536)
     for rep in range(3):
         t0 = time.time(); s = T.solve_batch_host(x0, obs, n); dt = time.time() - t0
-        print(f"MC 65536: e2e {dt*1e3:.1f} ms kernel {T.last_kernel_ms():.2f} ms -> {65536/(T.last_kernel_ms()*1e-3):.3e} solves/s; status {np.bincount(s['status'],minlength=3)} rounds {s['iters'][:,0].mean():.2f} iters mean {s['iters'][:,1].mean():.0f} max {s['iters'][:,1].max()}")
+        print(f"MC 65536: e2e {dt*1e3:.1f} ms kernel {T.last_kernel_ms():.2f} ms -> {65536/(T.last_kernel_ms()*1e-3):.3e} solves/s; status {np.bincount(s['status'],minlength=3)} rounds {s['iters'][:,0].mean():.2f} iters mean {s['iters'][:,1].mean():.0f} max {s['iters'][:,1].max()} passes {T.last_pass_ms()}")
     tf, ms = T.measure_fp64_peak()
     print(f"fp64 DFMA peak {tf:.2f} TFLOP/s ({ms:.2f} ms)")
     x1 = x0[:1]; 
