@@ -15,7 +15,9 @@
 
 namespace mpcb {
 
-constexpr int SOLVE_THREADS = 128;  // problems per CTA; 255 registers/thread -> 2 CTAs per SM
+constexpr int SOLVE_THREADS = 64;   // problems per CTA; 70 KB of shared memory per CTA -> 3 CTAs (6 warps) per SM
+using SolveStore = Store<SOLVE_THREADS>;
+constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::DOUBLES * SOLVE_THREADS;
 constexpr int EVAL_THREADS = 128;
 
 // ------------------------------------------------------------------------------------------------
@@ -25,7 +27,7 @@ constexpr int EVAL_THREADS = 128;
 //               are appended to fb_list / fb_count instead of being written out.
 // ------------------------------------------------------------------------------------------------
 template <bool FIRST_PASS>
-__global__ void __launch_bounds__(SOLVE_THREADS, 2)
+__global__ void __launch_bounds__(SOLVE_THREADS, 3)
 mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
                   const int* __restrict__ idx, const int* __restrict__ n_idx,
                   const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
@@ -50,7 +52,9 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
     pb.obs[0][0] = pb.obs[0][1] = pb.obs[1][0] = pb.obs[1][1] = 0.0;
     pb.n_obs = 0;
   }
-  SolveOut so = solve_one(T, P, pb, live);
+  extern __shared__ double solve_smem[];
+  const SolveStore st(solve_smem + threadIdx.x);
+  SolveOut so = solve_one<!FIRST_PASS>(T, P, pb, st, live);
   if (!live) return;
   if (FIRST_PASS && so.status == MPCB_MAXITER) {                   // not certified: leave it to the robust pass
     fb_list[atomicAdd(fb_count, 1)] = b;
@@ -162,13 +166,13 @@ mpcb_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
     pb.n_obs = 0;
     pb.obs[0][0] = pb.obs[0][1] = pb.obs[1][0] = pb.obs[1][1] = 0.0;
 #pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int j = 0; j < NH; ++j) pb.base[k][j] = 0.0;
+    for (int j = 0; j <= NH; ++j) pb.hint[j] = 1;
+    double buf[Store<1>::DOUBLES];
+    const Store<1> st(buf);
     double cv;
-    linearise(T, P, pb, cv);
-    // Export what the solver actually consumes: H (55), q (10), D/O rows (80), lane_c (12) packed into the
-    // 150-double Jr slot:  [0:55) H, [55:65) q, [65:105) D, [105:145) O, [145:150) unused (zero).
+    linearise(T, P, pb, st, cv);
+    // Export what the solver actually consumes: H (55), q (10), D/O rows (80) packed into the
+    // 150-double slot:  [0:55) H, [55:65) q, [65:105) D, [105:145) O, [145:150) unused (zero).
     double* o = Jr_out + (size_t)b * 150;
 #pragma unroll
     for (int i = 0; i < NTRI; ++i) o[i] = pb.H[i];
@@ -177,7 +181,10 @@ mpcb_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int c = 0; c < NV; ++c) { o[65 + 10 * j + c] = pb.D[j][c]; o[105 + 10 * j + c] = pb.O[j][c]; }
+      for (int c = 0; c < NV; ++c) {
+        o[65 + 10 * j + c] = (c < 2 * (j + 1)) ? st.D[doff(j) + c] : 0.0;
+        o[105 + 10 * j + c] = (c < 2 * (j + 1)) ? st.O[doff(j) + c] : 0.0;
+      }
 #pragma unroll
     for (int i = 145; i < 150; ++i) o[i] = 0.0;
   }
@@ -376,25 +383,27 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
     if (cudaMalloc(&h->fb, sizeof(int) * ((size_t)B + 1)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
     h->fb_cap = B;
   }
+  CK(cudaFuncSetAttribute(mpcb_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+  CK(cudaFuncSetAttribute(mpcb_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
   CK(cudaEventRecord(h->ev0, st));
   if (h->params.fast_pass) {
     int* fb_count = h->fb;
     int* fb_list = h->fb + 1;
     CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
-    mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, 0, st>>>(h->dt, h->dp_fast, B, nullptr, nullptr, x0, obs_sv, n_obs,
+    mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp_fast, B, nullptr, nullptr, x0, obs_sv, n_obs,
                                                            U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
                                                            active_out, fb_list, fb_count);
     CK(cudaGetLastError());
     CK(cudaEventRecord(h->ev_mid, st));
     // second pass over whatever the first did not certify; CTAs beyond the list length exit at once
-    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, 0, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs,
+    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs,
                                                             U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
                                                             active_out, nullptr, nullptr);
     CK(cudaGetLastError());
     h->launches += 2;
   } else {
     CK(cudaEventRecord(h->ev_mid, st));
-    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, 0, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
+    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
                                                             U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
                                                             active_out, nullptr, nullptr);
     CK(cudaGetLastError());

@@ -57,7 +57,7 @@ struct DevParams {
   double alpha_lane[3];// 0, wheelbase/2, wheelbase
   double brake_lookahead, brake_guess;
   int max_rounds, max_segments, segment_iters;
-  int n_rung, e_init, hysteresis, drop_all, up_step, trust_cert;
+  int n_rung, e_init, hysteresis, drop_all, up_step, trust_cert, init_iters, staged;
   double lad[MAXRUNG]; // step-size ladder rho_lo * fac^k (capped at rho_hi)
   double lad_ratio[MAXRUNG]; // lad[k-1]/lad[k] (k>=1): rescale of (v - z) when a row moves up one rung
   double relax;        // ADMM over-relaxation alpha
@@ -85,6 +85,45 @@ MPCB_HD void lookup_state(const DevTable& T, double s, double (&val)[4], double 
     return;
   }
   const int i = seg_index(T.s, T.K, s);
+  const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
+  const double inv = 1.0 / (x_hi - x_lo);
+  const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
+  double ylo[4], yhi[4];
+#if defined(__CUDA_ARCH__)
+  {
+    const double2* yl = reinterpret_cast<const double2*>(T.y + 4 * (i - 1));
+    const double2 l0 = __ldg(yl), l1 = __ldg(yl + 1), h0 = __ldg(yl + 2), h1 = __ldg(yl + 3);
+    ylo[0] = l0.x; ylo[1] = l0.y; ylo[2] = l1.x; ylo[3] = l1.y;
+    yhi[0] = h0.x; yhi[1] = h0.y; yhi[2] = h1.x; yhi[3] = h1.y;
+  }
+#else
+  for (int c = 0; c < 4; ++c) { ylo[c] = T.y[4 * (i - 1) + c]; yhi[c] = T.y[4 * i + c]; }
+#endif
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    val[c] = wl * yhi[c] + wr * ylo[c];
+    slope[c] = (yhi[c] - ylo[c]) * inv;
+  }
+}
+
+// Same as lookup_state, with the table segment remembered between calls: consecutive predicted positions (and the
+// same step in the next linearisation round) land in the same or a neighbouring segment, so a short walk from the
+// previous index replaces the binary search.  `hint` is updated.
+MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], double (&slope)[4], int& hint) {
+  if (s >= T.s_max) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { val[c] = T.last[c]; slope[c] = 0.0; }
+    return;
+  }
+  int i = hint < 1 ? 1 : (hint > T.K - 1 ? T.K - 1 : hint);
+  bool found = false;
+  for (int t = 0; t < 6 && !found; ++t) {
+    if (i < T.K - 1 && MPCB_LDG(T.s + i) < s) ++i;
+    else if (i > 1 && MPCB_LDG(T.s + i - 1) >= s) --i;
+    else found = true;
+  }
+  if (!found) i = seg_index(T.s, T.K, s);
+  hint = i;
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double inv = 1.0 / (x_hi - x_lo);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);

@@ -25,7 +25,7 @@ inline void default_params(mpcb_params* p) {
   p->rho_lo = 0.1; p->rho_hi = 1e4; p->rho_init = 1.0;
   p->alpha = 1.6;
   p->eps_prim = 1e-9; p->eps_dual = 1e-8; p->eps_infeas = 1e-4;
-  p->step_tol = 1e-7; p->feas_tol = 1e-6;
+  p->step_tol = 1e-5; p->feas_tol = 1e-6;
   p->fast_pass = 1;
   p->fast_rho_off = 1e-9; p->fast_rho_on = 1e6;
   p->fast_max_rounds = 6; p->fast_max_segments = 4; p->fast_segment_iters = 2;
@@ -84,6 +84,8 @@ inline int derive_params(const mpcb_params& p, DevParams& d, bool fast = false) 
 #endif
   d.relax = p.alpha;
   d.trust_cert = 1;
+  d.staged = 0;
+  d.init_iters = p.segment_iters;
   if (fast) {
     if (!(p.fast_rho_off > 0) || !(p.fast_rho_on > p.fast_rho_off) || p.fast_max_rounds < 1 ||
         p.fast_max_segments < 1 || p.fast_segment_iters < 1)
@@ -93,6 +95,15 @@ inline int derive_params(const mpcb_params& p, DevParams& d, bool fast = false) 
     d.n_rung = 2; d.e_init = 0; d.hysteresis = 0; d.drop_all = 1; d.up_step = 1;
     d.relax = 1.0;
     d.trust_cert = 0;
+    d.init_iters = d.segment_iters;
+#ifndef __CUDACC__
+    if (getenv("MPCB_STAGED")) d.staged = atoi(getenv("MPCB_STAGED"));
+    if (getenv("MPCB_INIT_RHO") && atof(getenv("MPCB_INIT_RHO")) > 0) {
+      d.lad[2] = atof(getenv("MPCB_INIT_RHO"));
+      d.e_init = 2;
+      d.init_iters = getenv("MPCB_INIT_ITERS") ? atoi(getenv("MPCB_INIT_ITERS")) : 4;
+    }
+#endif
     d.max_rounds = p.fast_max_rounds; d.max_segments = p.fast_max_segments; d.segment_iters = p.fast_segment_iters;
   }
   d.eps_p = p.eps_prim; d.eps_d = p.eps_dual; d.eps_inf = p.eps_infeas;

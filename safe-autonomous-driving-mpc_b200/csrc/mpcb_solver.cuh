@@ -1,18 +1,26 @@
-// mpcb_solver.cuh -- per-thread Gauss-Newton SQP with an OSQP-style ADMM QP solver.
+// mpcb_solver.cuh -- per-thread Gauss-Newton SQP with an OSQP-style ADMM QP solver (one thread = one problem).
 //
 // QP of one linearisation round, in the absolute variable x = U+ (SURVEY.md A.1 for the formulation):
-//     min 1/2 x'Hx + q'x   s.t.  lo <= A x <= hi ,   H = I*2w_u + 2 J'WJ  (Gauss-Newton),  q = g - H U
-// Rows of A (M = 47):
-//     0..9    box           x_i in [u_min, u_max]                                (trajectory_tracking.py:249)
-//     10..21  lane          (D_j + alpha_a O_j) x, j = 2..5, a = 0..2            (:171-189; step 1 is constant in U)
-//     22..26  speed         v_j - v0 = h sum_{i<j} b_i >= -v0                    (:207)
-//     27+10k+2(j-1)+{0,1}   obstacle k, step j: R1 = S_j <= base - safe,  R2 = S_j + tgap (v_j - v0) <= base - tgap v0
-//                           with S_j = s_j - s0 - j h v0 (the max(.,.) of :201 split into two affine rows, A.1)
+//     min 1/2 x'Hx + q'x   s.t.  lo <= A x <= hi ,   H = diag(2 w_u) + 2 J'WJ  (Gauss-Newton),  q = g - H U
+// Rows of A (M = 41), never stored densely:
+//     0..9    box      x_i in [u_min, u_max]                                         (trajectory_tracking.py:249)
+//     10..17  lane     (D_j + alpha O_j) x, j = 2..5, alpha in {0, wheelbase}        (:171-189)
+//                      -- step 1 does not depend on U; the alpha = wheelbase/2 row is implied by the two outer ones
+//                         (|d + alpha o| is convex in alpha), so it is not a row of the QP
+//     18..22  speed    v_j - v0 = h sum_{i<j} b_i >= -v0                             (:207)
+//     23+9k.. obstacle k:  R1_j (j = 2..5): S_j <= base_j - safe ;  R2_j (j = 1..5): S_j + tgap (v_j - v0) <= base_j - tgap v0
+//                      with S_j = s_j - s0 - j h v0: the max(.,.) of :201 split into two affine rows
 // ADMM with sigma = 0 and relaxation alpha in single-vector form (v = z_relaxed + y/rho; z = clip(v), y = rho (v - z)):
-//     x  = K^-1 (A' rho (2 clip(v) - v) - q),  K = H + A' diag(rho) A ;   v += alpha (A x - clip(v))
-// rho_i = lad[e_i] / max(|a_i|^2, floor); every segment (segment_iters iterations) a row that stayed active
-// moves one rung up the ladder, a row that stayed inactive one rung down, K is refactored, residuals and the
-// OSQP primal-infeasibility certificate are evaluated.
+//     x  = K^-1 (A' rho (2 clip(v) - v) - q),  K = H + A' diag(rho) A = L L' ;   v += alpha (A x - clip(v))
+// rho_r = lad[e_r] / max(|a_r|^2, floor).  A segment = factorisation + a few iterations, the last of which also
+// evaluates residuals, the active set, the step-size policy and (robust pass) OSQP's infeasibility certificate.
+// Two policies run on this machinery (mpcb_params.h): the first pass uses two rungs {~0, large} -- inactive rows
+// exert no force, active rows are near-equalities: a primal-dual active-set iteration with augmented-Lagrangian
+// inner solves -- and hands whatever it cannot close to the robust pass, which walks a x10 ladder with hysteresis.
+//
+// Data placement: the per-row vectors (v, rho, obstacle bounds) and the lane sensitivities D, O live in a strided
+// store (shared memory on the GPU: element i of thread t at base[i * CTA + t], conflict free), the 10x10 factor,
+// H, q and the iterate in registers / local memory.
 #pragma once
 #include <type_traits>
 
@@ -29,16 +37,46 @@
 
 namespace mpcb {
 
-constexpr int M_LANE = 12;
-constexpr int ROW_LANE = 10, ROW_V = 22, ROW_OBS = 27, M_ROWS = 47;
+constexpr int N_LANE = 8;
+constexpr int ROW_LANE = 10, ROW_V = 18, ROW_OBS = 23, N_OBSROW = 9, M_ROWS = 41;
+constexpr int N_DO = 20;   // flat storage of d(d_j)/dU (resp. o_j), j = 2..5: supports 2, 4, 6, 8
 constexpr double NRM2_FLOOR = 1e-2;
+
+__host__ __device__ constexpr int doff(int jj) { return jj * (jj + 1); }               // 0, 2, 6, 12
+__host__ __device__ constexpr int row_r1(int k, int j) { return ROW_OBS + N_OBSROW * k + (j - 2); }   // j = 2..5
+__host__ __device__ constexpr int row_r2(int k, int j) { return ROW_OBS + N_OBSROW * k + 4 + (j - 1); }  // j = 1..5
+
+// On the GPU the store is accessed through volatile pointers: every access is a real shared-memory load / store.
+// (Without it the compiler promotes the whole store to registers across the iteration loop and then spills those
+// registers to local memory -- i.e. through L1 to L2/DRAM -- which is exactly what the store is there to avoid.)
+#if defined(__CUDA_ARCH__) && !defined(MPCB_STORE_PLAIN)
+typedef volatile double store_t;
+#else
+typedef double store_t;
+#endif
+template <int S>
+struct Col {
+  store_t* p;
+  MPCB_HD store_t& operator[](int i) const { return p[i * S]; }
+};
+
+// strided per-thread store; S = 1 on the host, S = CTA size in shared memory
+template <int S>
+struct Store {
+  static constexpr int DOUBLES = M_ROWS + M_ROWS + 2 * N_OBSROW + 2 * N_DO;
+  Col<S> v;      // [41] ADMM state
+  Col<S> rho;    // [41] step sizes of the current factorisation
+  Col<S> hio;    // [18] upper bounds of the obstacle rows (BIG: row absent or dropped)
+  Col<S> D, O;   // [20] lane sensitivities
+  MPCB_HD explicit Store(double* b)
+      : v{b}, rho{b + M_ROWS * S}, hio{b + 2 * M_ROWS * S}, D{b + (2 * M_ROWS + 2 * N_OBSROW) * S},
+        O{b + (2 * M_ROWS + 2 * N_OBSROW + N_DO) * S} {}
+};
 
 struct Rungs {  // 4-bit ladder index per row
   unsigned int w[6];
-  __device__ __forceinline__ int get(int r) const { return (w[r >> 3] >> ((r & 7) * 4)) & 15; }
-  __device__ __forceinline__ void set(int r, int e) {
-    w[r >> 3] = (w[r >> 3] & ~(15u << ((r & 7) * 4))) | ((unsigned)e << ((r & 7) * 4));
-  }
+  MPCB_HD int get(int r) const { return (w[r >> 3] >> ((r & 7) * 4)) & 15; }
+  MPCB_HD void set(int r, int e) { w[r >> 3] = (w[r >> 3] & ~(15u << ((r & 7) * 4))) | ((unsigned)e << ((r & 7) * 4)); }
 };
 
 struct Problem {
@@ -51,29 +89,28 @@ struct Problem {
   double x[NV];
   // QP data of the current round
   double H[NTRI];
-  double Kinv[NTRI];
   double q[NV];
-  double D[4][NV], O[4][NV];   // d(d_j)/dU, d(o_j)/dU for j = 2..5 (only the first 2(j-1) entries are non-zero)
-  double lane_c[M_LANE];       // row value offset: (d_j + alpha o_j)(U) - a.U
-  double lane_inrm[M_LANE];
-  double base[2][NH];          // s_obs_k + v_obs_k j h - s0 - j h v0
-  // ADMM state
-  double vb[NV], vl[M_LANE], vv[NH], vo[2][NH][2];
+  double lane_c[N_LANE];      // row value offset: (d_j + alpha o_j)(U) - a.U
+  double lane_inrm[N_LANE];
+  double lov[NH];             // lower bound of the speed rows (-BIG when dropped)
+  // factor of K
+  double L[NTRI];
+  double rdiag[NV];
+  // policy state
   Rungs E;
   unsigned long long act_prev;
+  int hint[NH + 1];           // table segment of s_j found by the previous lookup
 };
 
-// ---- bounds per row type ------------------------------------------------------------------------
-__device__ __forceinline__ double clipd(double v, double lo, double hi) { return fmin(fmax(v, lo), hi); }
+MPCB_HD double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
+MPCB_HD double dmax(double a, double b) { return a > b ? a : b; }
 
 // ------------------------------------------------------------------------------------------------
 // Linearisation: rollout with forward sensitivities at pb.U; fills H, q, D, O, lane_c, lane_inrm.
-// Returns the worst violation among rows that U cannot influence (step-1 lane rows, step-1 "gap - safe"
-// row) through const_viol.
+// const_viol = worst violation among the lane rows of step 1 (they do not depend on U).
 // ------------------------------------------------------------------------------------------------
 template <int L>
-__device__ __forceinline__ void rank1(double (&H)[NTRI], const double (&a)[NV], double w) {
-  // H += w * a a'  restricted to the leading L x L block
+MPCB_HD void rank1(double (&H)[NTRI], const double (&a)[NV], double w) {
 #pragma unroll
   for (int i = 0; i < L; ++i) {
     const double wa = w * a[i];
@@ -83,10 +120,9 @@ __device__ __forceinline__ void rank1(double (&H)[NTRI], const double (&a)[NV], 
 }
 
 template <int J>  // residual rows of step J (1..5): accumulate H and g
-__device__ __forceinline__ void accumulate_step(const DevParams& P, Problem& pb, double (&g)[NV],
-                                                const double (&dD)[NV], const double (&dO)[NV],
-                                                const double (&Xj)[5], const double (&val)[4],
-                                                const double (&slope)[4]) {
+MPCB_HD void accumulate_step(const DevParams& P, Problem& pb, double (&g)[NV], const double (&dD)[NV],
+                             const double (&dO)[NV], const double (&Xj)[5], const double (&val)[4],
+                             const double (&slope)[4]) {
   constexpr int L = 2 * (J - 1);  // support of dD, dO, ds_J
   const double h = P.h;
   double Jd[NV], Jo[NV], Jv[NV];
@@ -120,18 +156,16 @@ __device__ __forceinline__ void accumulate_step(const DevParams& P, Problem& pb,
   }
 }
 
-template <int J>  // lane rows of step J (2..5)
-__device__ __forceinline__ void lane_rows(const DevParams& P, Problem& pb, const double (&dD)[NV],
-                                          const double (&dO)[NV], const double (&Xj)[5]) {
+template <int J, int S>  // lane rows of step J (2..5)
+MPCB_HD void lane_rows(const DevParams& P, Problem& pb, const Store<S>& st, const double (&dD)[NV],
+                       const double (&dO)[NV], const double (&Xj)[5]) {
   constexpr int L = 2 * (J - 1);
-#pragma unroll
-  for (int c = 0; c < NV; ++c) {
-    pb.D[J - 2][c] = (c < L) ? dD[c] : 0.0;
-    pb.O[J - 2][c] = (c < L) ? dO[c] : 0.0;
-  }
+  constexpr int o = doff(J - 2);
   double dU = 0.0, oU = 0.0, dd = 0.0, dox = 0.0, oo = 0.0;
 #pragma unroll
   for (int c = 0; c < L; ++c) {
+    st.D[o + c] = dD[c];
+    st.O[o + c] = dO[c];
     dU = fma(dD[c], pb.U[c], dU);
     oU = fma(dO[c], pb.U[c], oU);
     dd = fma(dD[c], dD[c], dd);
@@ -139,15 +173,16 @@ __device__ __forceinline__ void lane_rows(const DevParams& P, Problem& pb, const
     oo = fma(dO[c], dO[c], oo);
   }
 #pragma unroll
-  for (int a = 0; a < 3; ++a) {
-    const double al = P.alpha_lane[a];
-    pb.lane_c[3 * (J - 2) + a] = (Xj[1] + al * Xj[2]) - (dU + al * oU);
+  for (int a = 0; a < 2; ++a) {
+    const double al = a ? P.alpha_lane[2] : 0.0;
+    pb.lane_c[2 * (J - 2) + a] = (Xj[1] + al * Xj[2]) - (dU + al * oU);
     const double n2 = dd + 2.0 * al * dox + al * al * oo;
-    pb.lane_inrm[3 * (J - 2) + a] = 1.0 / fmax(n2, NRM2_FLOOR);
+    pb.lane_inrm[2 * (J - 2) + a] = 1.0 / dmax(n2, NRM2_FLOOR);
   }
 }
 
-__device__ __forceinline__ void linearise(const DevTable& T, const DevParams& P, Problem& pb, double& const_viol) {
+template <int S>
+MPCB_HD void linearise(const DevTable& T, const DevParams& P, Problem& pb, const Store<S>& st, double& const_viol) {
   const double h = P.h;
 #pragma unroll
   for (int i = 0; i < NTRI; ++i) pb.H[i] = 0.0;
@@ -168,7 +203,6 @@ __device__ __forceinline__ void linearise(const DevTable& T, const DevParams& P,
     constexpr int j = decltype(jtag)::value;  // step j -> j+1
     const double s = X[0], d = X[1], o = X[2], k = X[3], v = X[4];
     const double kk = k - val[2];
-    // sensitivities first (they use the old state)
     double nD[NV], nO[NV];
 #pragma unroll
     for (int c = 0; c < NV; ++c) { nD[c] = dD[c]; nO[c] = dO[c]; }
@@ -191,29 +225,29 @@ __device__ __forceinline__ void linearise(const DevTable& T, const DevParams& P,
     X[4] = v + h * pb.U[2 * j + 1];
   };
 
-  lookup_state(T, X[0], val, slope);
+  lookup_state_hint(T, X[0], val, slope, pb.hint[0]);
   advance(std::integral_constant<int, 0>{});
   // step 1: rows constant in U
-  lookup_state(T, X[0], val, slope);
+  lookup_state_hint(T, X[0], val, slope, pb.hint[1]);
   accumulate_step<1>(P, pb, g, dD, dO, X, val, slope);
-#pragma unroll
-  for (int a = 0; a < 3; ++a) cv = fmax(cv, fabs(X[1] + P.alpha_lane[a] * X[2]) - P.sld);
+  cv = dmax(cv, fabs(X[1]) - P.sld);
+  cv = dmax(cv, fabs(X[1] + P.alpha_lane[2] * X[2]) - P.sld);
   advance(std::integral_constant<int, 1>{});
-  lookup_state(T, X[0], val, slope);
+  lookup_state_hint(T, X[0], val, slope, pb.hint[2]);
   accumulate_step<2>(P, pb, g, dD, dO, X, val, slope);
-  lane_rows<2>(P, pb, dD, dO, X);
+  lane_rows<2>(P, pb, st, dD, dO, X);
   advance(std::integral_constant<int, 2>{});
-  lookup_state(T, X[0], val, slope);
+  lookup_state_hint(T, X[0], val, slope, pb.hint[3]);
   accumulate_step<3>(P, pb, g, dD, dO, X, val, slope);
-  lane_rows<3>(P, pb, dD, dO, X);
+  lane_rows<3>(P, pb, st, dD, dO, X);
   advance(std::integral_constant<int, 3>{});
-  lookup_state(T, X[0], val, slope);
+  lookup_state_hint(T, X[0], val, slope, pb.hint[4]);
   accumulate_step<4>(P, pb, g, dD, dO, X, val, slope);
-  lane_rows<4>(P, pb, dD, dO, X);
+  lane_rows<4>(P, pb, st, dD, dO, X);
   advance(std::integral_constant<int, 4>{});
-  lookup_state(T, X[0], val, slope);
+  lookup_state_hint(T, X[0], val, slope, pb.hint[5]);
   accumulate_step<5>(P, pb, g, dD, dO, X, val, slope);
-  lane_rows<5>(P, pb, dD, dO, X);
+  lane_rows<5>(P, pb, st, dD, dO, X);
 
   // q = g - H U
 #pragma unroll
@@ -223,62 +257,149 @@ __device__ __forceinline__ void linearise(const DevTable& T, const DevParams& P,
     for (int j = 0; j < NV; ++j) acc = fma(-pb.H[i >= j ? tri(i, j) : tri(j, i)], pb.U[j], acc);
     pb.q[i] = acc;
   }
-  // constant obstacle row (step 1, "gap - safe"): base_1 - obs_safe >= 0
-#pragma unroll
-  for (int k = 0; k < 2; ++k)
-    if (k < pb.n_obs) cv = fmax(cv, P.obs_safe - pb.base[k][0]);
   const_viol = cv;
 }
 
 // ------------------------------------------------------------------------------------------------
-// K = H + A' diag(rho) A  ->  Kinv (explicit inverse through Cholesky), all in packed lower triangles.
+// Row walk.  f(r, zt_r, lo, hi) is called for every row in index order with the row value zt_r = (A x)_r.
+// Absent obstacles keep their rows (bounds BIG, rho 0 by construction), so the walk has no data-dependent branch.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double row_rho(const DevParams& P, const Rungs& E, int r, double inrm) {
-  return P.lad[E.get(r)] * inrm;
-}
-
-__device__ __forceinline__ void factor(const DevParams& P, Problem& pb) {
+template <int S, class F>
+MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const Store<S>& st, const double (&x)[NV], F&& f) {
   const double h = P.h;
-  double K[NTRI];
 #pragma unroll
-  for (int i = 0; i < NTRI; ++i) K[i] = pb.H[i];
-#pragma unroll
-  for (int i = 0; i < NV; ++i) K[tri(i, i)] += row_rho(P, pb.E, i, 1.0);
-  // lane rows of step j:  sum_a rho_a (D + al_a O)(D + al_a O)' = D (r0 D + r1 O)' + O (r1 D + r2 O)'
+  for (int i = 0; i < NV; ++i) f(i, x[i], P.umin[i & 1], P.umax[i & 1]);
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
-    const int L = 2 * (jj + 1);
-    double r0 = 0.0, r1 = 0.0, r2 = 0.0;
+    double dj = 0.0, oj = 0.0;
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-      const double rho = row_rho(P, pb.E, ROW_LANE + 3 * jj + a, pb.lane_inrm[3 * jj + a]);
-      const double al = P.alpha_lane[a];
-      r0 += rho; r1 = fma(rho, al, r1); r2 = fma(rho, al * al, r2);
+    for (int c = 0; c < 2 * (jj + 1); ++c) {
+      dj = fma(st.D[doff(jj) + c], x[c], dj);
+      oj = fma(st.O[doff(jj) + c], x[c], oj);
     }
+    f(ROW_LANE + 2 * jj, dj, -P.sld - pb.lane_c[2 * jj], P.sld - pb.lane_c[2 * jj]);
+    f(ROW_LANE + 2 * jj + 1, fma(P.alpha_lane[2], oj, dj), -P.sld - pb.lane_c[2 * jj + 1],
+      P.sld - pb.lane_c[2 * jj + 1]);
+  }
+  double cum = 0.0, Sj = 0.0;
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      if (i < L) {
-        const double p = r0 * pb.D[jj][i] + r1 * pb.O[jj][i];
-        const double t = r1 * pb.D[jj][i] + r2 * pb.O[jj][i];
+  for (int j = 1; j <= NH; ++j) {
+    // S_j = h sum_{m<j} (v_m - v0);  cum = v_j - v0
+    if (j > 1) Sj = fma(h, cum, Sj);
+    cum = fma(h, x[2 * (j - 1) + 1], cum);
+    f(ROW_V + j - 1, cum, pb.lov[j - 1], BIG);
 #pragma unroll
-        for (int j = 0; j <= i; ++j) K[tri(i, j)] = fma(p, pb.D[jj][j], fma(t, pb.O[jj][j], K[tri(i, j)]));
+    for (int k = 0; k < 2; ++k) {
+      if (j > 1) f(row_r1(k, j), Sj, -BIG, st.hio[N_OBSROW * k + (j - 2)]);
+      f(row_r2(k, j), fma(P.tgap, cum, Sj), -BIG, st.hio[N_OBSROW * k + 4 + (j - 1)]);
+    }
+  }
+}
+
+// out += A' w, fed row by row in the order for_rows walks (no per-row array needs to be kept):
+//   box rows add straight into out; a lane step's two rows are folded into (wD, wO) and applied when the second
+//   one arrives; speed / obstacle rows are folded into per-step sums Tv, Ts and applied by finish().
+template <int S>
+struct AtAcc {
+  const DevParams& P;
+  const Store<S>& st;
+  double (&out)[NV];
+  double w0;
+  double Tv[NH], Ts[NH];
+  MPCB_HD AtAcc(const DevParams& P_, const Store<S>& st_, double (&out_)[NV]) : P(P_), st(st_), out(out_), w0(0.0) {
+#pragma unroll
+    for (int j = 0; j < NH; ++j) { Tv[j] = 0.0; Ts[j] = 0.0; }
+  }
+  MPCB_HD void add(int r, double w) {     // r is a compile-time constant after unrolling
+    if (r < ROW_LANE) {
+      out[r] += w;
+    } else if (r < ROW_V) {
+      const int jj = (r - ROW_LANE) >> 1;
+      if (((r - ROW_LANE) & 1) == 0) {
+        w0 = w;
+      } else {
+        const double wD = w0 + w, wO = P.alpha_lane[2] * w;
+#pragma unroll
+        for (int c = 0; c < NV; ++c)
+          if (c < 2 * (jj + 1)) out[c] = fma(st.D[doff(jj) + c], wD, fma(st.O[doff(jj) + c], wO, out[c]));
+      }
+    } else if (r < ROW_OBS) {
+      Tv[r - ROW_V] += w;
+    } else {
+      const int q = (r - ROW_OBS) % N_OBSROW;
+      if (q < 4) {
+        Ts[q + 1] += w;                       // R1_j, j = q + 2
+      } else {
+        Tv[q - 4] = fma(P.tgap, w, Tv[q - 4]);   // R2_j, j = q - 3
+        Ts[q - 4] += w;
       }
     }
   }
-  // constant-coefficient rows act on the b entries only: Kb[i][k] += sum_r rho_r c_r[i] c_r[k]
-  double Kb[15];
+  MPCB_HD void finish() {
+    // b_i += h sum_{j>i} Tv[j] + h^2 sum_{j>=i+2} (j-1-i) Ts[j]      (j is 1-based; arrays are j-1)
+    const double h = P.h;
+    double sv = 0.0, ps = 0.0, cs = 0.0;
 #pragma unroll
-  for (int i = 0; i < 15; ++i) Kb[i] = 0.0;
+    for (int i = NH - 1; i >= 0; --i) {
+      sv += Tv[i];
+      out[2 * i + 1] = fma(h, sv, fma(h * h, cs, out[2 * i + 1]));
+      ps += Ts[i];
+      cs += ps;
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// rho_r from the rungs, then K = H + A' diag(rho) A = L L'  (packed lower triangle, reciprocal diagonal kept)
+// ------------------------------------------------------------------------------------------------
+template <int S>
+MPCB_HD void factor(const DevParams& P, Problem& pb, const Store<S>& st) {
+  const double h = P.h;
+  // step sizes of this factorisation
+#pragma unroll
+  for (int i = 0; i < NV; ++i) st.rho[i] = P.lad[pb.E.get(i)];
+#pragma unroll
+  for (int r = 0; r < N_LANE; ++r) st.rho[ROW_LANE + r] = P.lad[pb.E.get(ROW_LANE + r)] * pb.lane_inrm[r];
 #pragma unroll
   for (int j = 1; j <= NH; ++j) {
-    const double rv = row_rho(P, pb.E, ROW_V + j - 1, P.inrm_v[j - 1]);
+    st.rho[ROW_V + j - 1] = P.lad[pb.E.get(ROW_V + j - 1)] * P.inrm_v[j - 1];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const bool on = k < pb.n_obs;
+      if (j > 1) st.rho[row_r1(k, j)] = on ? P.lad[pb.E.get(row_r1(k, j))] * P.inrm_r1[j - 1] : 0.0;
+      st.rho[row_r2(k, j)] = on ? P.lad[pb.E.get(row_r2(k, j))] * P.inrm_r2[j - 1] : 0.0;
+    }
+  }
+  double (&K)[NTRI] = pb.L;
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) K[i] = pb.H[i];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) K[tri(i, i)] += st.rho[i];
+  // lane rows of step j:  rho0 D D' + rho1 (D + wb O)(D + wb O)' = D (r0 D + r1 O)' + O (r1 D + r2 O)'
+#pragma unroll
+  for (int jj = 0; jj < 4; ++jj) {
+    const double rho0 = st.rho[ROW_LANE + 2 * jj], rho1 = st.rho[ROW_LANE + 2 * jj + 1];
+    const double wb = P.alpha_lane[2];
+    const double r0 = rho0 + rho1, r1 = rho1 * wb, r2 = rho1 * wb * wb;
+#pragma unroll
+    for (int i = 0; i < 2 * (jj + 1); ++i) {
+      const double Di = st.D[doff(jj) + i], Oi = st.O[doff(jj) + i];
+      const double p = r0 * Di + r1 * Oi;
+      const double t = r1 * Di + r2 * Oi;
+#pragma unroll
+      for (int j = 0; j <= i; ++j)
+        K[tri(i, j)] = fma(p, st.D[doff(jj) + j], fma(t, st.O[doff(jj) + j], K[tri(i, j)]));
+    }
+  }
+  // constant-coefficient rows act on the b entries only: Kb[i][k] += sum_r rho_r c_r[i] c_r[k]
+#pragma unroll
+  for (int j = 1; j <= NH; ++j) {
+    const double rv = st.rho[ROW_V + j - 1];
     double r1 = 0.0, r2 = 0.0;   // summed over obstacles (same coefficient vectors)
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (k < pb.n_obs) {
-        if (j > 1) r1 += row_rho(P, pb.E, ROW_OBS + 10 * k + 2 * (j - 1), P.inrm_r1[j - 1]);
-        r2 += row_rho(P, pb.E, ROW_OBS + 10 * k + 2 * (j - 1) + 1, P.inrm_r2[j - 1]);
-      }
+      if (j > 1) r1 += st.rho[row_r1(k, j)];
+      r2 += st.rho[row_r2(k, j)];
     }
 #pragma unroll
     for (int i = 0; i < j; ++i) {
@@ -288,17 +409,11 @@ __device__ __forceinline__ void factor(const DevParams& P, Problem& pb) {
       for (int k = 0; k <= i; ++k) {
         const double cs_k = h * h * (double)(j - 1 - k);
         const double c2_k = cs_k + P.tgap * h;
-        Kb[tri(i, k)] += rv * (h * h) + r1 * (cs_i * cs_k) + r2 * (c2_i * c2_k);
+        K[tri(2 * i + 1, 2 * k + 1)] += rv * (h * h) + r1 * (cs_i * cs_k) + r2 * (c2_i * c2_k);
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < NH; ++i)
-#pragma unroll
-    for (int k = 0; k <= i; ++k) K[tri(2 * i + 1, 2 * k + 1)] += Kb[tri(i, k)];
-
   // Cholesky K = L L' in place (lower), keeping reciprocal diagonals
-  double rdiag[NV];
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
     double d = K[tri(j, j)];
@@ -306,7 +421,7 @@ __device__ __forceinline__ void factor(const DevParams& P, Problem& pb) {
     for (int k = 0; k < j; ++k) d = fma(-K[tri(j, k)], K[tri(j, k)], d);
     const double rs = rsqrt(d);
     K[tri(j, j)] = d * rs;
-    rdiag[j] = rs;
+    pb.rdiag[j] = rs;
 #pragma unroll
     for (int i = j + 1; i < NV; ++i) {
       double s = K[tri(i, j)];
@@ -315,262 +430,160 @@ __device__ __forceinline__ void factor(const DevParams& P, Problem& pb) {
       K[tri(i, j)] = s * rs;
     }
   }
-  // Linv (lower) in place of a second packed array
-  double Li[NTRI];
+}
+
+// x = K^-1 r through the factor (column-oriented substitutions: independent updates after every pivot)
+MPCB_HD void chol_solve(const Problem& pb, double (&r)[NV], double (&x)[NV]) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    Li[tri(j, j)] = rdiag[j];
+    r[j] *= pb.rdiag[j];
 #pragma unroll
-    for (int i = j + 1; i < NV; ++i) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = j; k < i; ++k) s = fma(-K[tri(i, k)], Li[tri(k, j)], s);
-      Li[tri(i, j)] = s * rdiag[i];
-    }
+    for (int i = j + 1; i < NV; ++i) r[i] = fma(-pb.L[tri(i, j)], r[j], r[i]);
   }
-  // Kinv = Linv' Linv
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
+  for (int j = NV - 1; j >= 0; --j) {
+    x[j] = r[j] * pb.rdiag[j];
 #pragma unroll
-    for (int j = 0; j <= i; ++j) {
-      double s = 0.0;
-#pragma unroll
-      for (int k = i; k < NV; ++k) s = fma(Li[tri(k, i)], Li[tri(k, j)], s);
-      pb.Kinv[tri(i, j)] = s;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// Row sweeps.  `f(row_index, v_ref, lo, hi, inrm)` is applied to every live row; the functor decides what
-// to do.  Constant rows (obstacle R1 at step 1) are not rows of the QP.
-// ------------------------------------------------------------------------------------------------
-template <class F>
-__device__ __forceinline__ void for_each_row(const DevParams& P, Problem& pb, F&& f) {
-#pragma unroll
-  for (int i = 0; i < NV; ++i) f(i, pb.vb[i], P.umin[i & 1], P.umax[i & 1], 1.0);
-#pragma unroll
-  for (int r = 0; r < M_LANE; ++r) f(ROW_LANE + r, pb.vl[r], -P.sld - pb.lane_c[r], P.sld - pb.lane_c[r], pb.lane_inrm[r]);
-#pragma unroll
-  for (int j = 0; j < NH; ++j) f(ROW_V + j, pb.vv[j], -pb.x0[4], BIG, P.inrm_v[j]);
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    if (k < pb.n_obs) {
-#pragma unroll
-      for (int j = 0; j < NH; ++j) {
-        if (j > 0) f(ROW_OBS + 10 * k + 2 * j, pb.vo[k][j][0], -BIG, pb.base[k][j] - P.obs_safe, P.inrm_r1[j]);
-        f(ROW_OBS + 10 * k + 2 * j + 1, pb.vo[k][j][1], -BIG, pb.base[k][j] - P.tgap * pb.x0[4], P.inrm_r2[j]);
-      }
-    }
+    for (int i = 0; i < j; ++i) r[i] = fma(-pb.L[tri(j, i)], x[j], r[i]);
   }
-}
-
-// out += A' w, where w is given per row type
-struct RowW {
-  double b[NV], l[M_LANE], v[NH], o[2][NH][2];
-};
-
-__device__ __forceinline__ void at_mul(const DevParams& P, const Problem& pb, const RowW& w, double (&out)[NV]) {
-  const double h = P.h;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) out[i] += w.b[i];
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const int L = 2 * (jj + 1);
-    double wD = 0.0, wO = 0.0;
-#pragma unroll
-    for (int a = 0; a < 3; ++a) { wD += w.l[3 * jj + a]; wO = fma(P.alpha_lane[a], w.l[3 * jj + a], wO); }
-#pragma unroll
-    for (int c = 0; c < NV; ++c)
-      if (c < L) out[c] = fma(pb.D[jj][c], wD, fma(pb.O[jj][c], wO, out[c]));
-  }
-  double Tv[NH], Ts[NH];
-#pragma unroll
-  for (int j = 0; j < NH; ++j) { Tv[j] = w.v[j]; Ts[j] = 0.0; }
-#pragma unroll
-  for (int k = 0; k < 2; ++k) {
-    if (k < pb.n_obs) {
-#pragma unroll
-      for (int j = 0; j < NH; ++j) {
-        Tv[j] = fma(P.tgap, w.o[k][j][1], Tv[j]);
-        Ts[j] += ((j > 0) ? w.o[k][j][0] : 0.0) + w.o[k][j][1];
-      }
-    }
-  }
-  // b_i += h sum_{j>i} Tv[j] + h^2 sum_{j>=i+2} (j-1-i) Ts[j]      (j is 1-based; arrays are j-1)
-  double sv = 0.0, ps = 0.0, cs = 0.0;
-#pragma unroll
-  for (int i = NH - 1; i >= 0; --i) {
-    sv += Tv[i];             // sum_{j-1 >= i}  <=> j > i
-    out[2 * i + 1] = fma(h, sv, fma(h * h, cs, out[2 * i + 1]));
-    ps += Ts[i];             // P_{j=i+1} = sum_{m>=i+1} Ts[m-1]
-    cs += ps;                // C_{i-1} = sum_{j>=i+1} P_j
-  }
-}
-
-// zt = A x per row type
-__device__ __forceinline__ void a_mul(const DevParams& P, const Problem& pb, const double (&x)[NV], RowW& zt) {
-  const double h = P.h;
-#pragma unroll
-  for (int i = 0; i < NV; ++i) zt.b[i] = x[i];
-#pragma unroll
-  for (int jj = 0; jj < 4; ++jj) {
-    const int L = 2 * (jj + 1);
-    double dj = 0.0, oj = 0.0;
-#pragma unroll
-    for (int c = 0; c < NV; ++c)
-      if (c < L) { dj = fma(pb.D[jj][c], x[c], dj); oj = fma(pb.O[jj][c], x[c], oj); }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) zt.l[3 * jj + a] = fma(P.alpha_lane[a], oj, dj);
-  }
-  double cum = 0.0, S = 0.0;
-#pragma unroll
-  for (int j = 0; j < NH; ++j) {
-    // S_{j+1} = h sum_{m=1..j} (v_m - v0)
-    if (j > 0) S = fma(h, zt.v[j - 1], S);
-    cum = fma(h, x[2 * j + 1], cum);
-    zt.v[j] = cum;
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-      zt.o[k][j][0] = S;
-      zt.o[k][j][1] = fma(P.tgap, cum, S);
-    }
-  }
-}
-
-__device__ __forceinline__ void sym_mul(const double (&Kinv)[NTRI], const double (&r)[NV], double (&x)[NV]) {
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    double acc = 0.0;
-#pragma unroll
-    for (int j = 0; j < NV; ++j) acc = fma(Kinv[i >= j ? tri(i, j) : tri(j, i)], r[j], acc);
-    x[i] = acc;
-  }
-}
-
-// row-type accessor into a RowW by global row index (compile-time after unrolling)
-__device__ __forceinline__ double& roww(RowW& w, int r) {
-  if (r < ROW_LANE) return w.b[r];
-  if (r < ROW_V) return w.l[r - ROW_LANE];
-  if (r < ROW_OBS) return w.v[r - ROW_V];
-  const int q = r - ROW_OBS;
-  return w.o[q / 10][(q % 10) / 2][q & 1];
 }
 
 struct SegStats { double rp, rd, nd, atdy, sup, bad; };
 
-// One ADMM iteration.  LAST additionally evaluates residuals, certificate quantities and updates the ladder.
-template <bool LAST>
-__device__ __forceinline__ void admm_iter(const DevParams& P, Problem& pb, SegStats& st) {
-  RowW w;
-  for_each_row(P, pb, [&](int r, double& v, double lo, double hi, double inrm) {
-    const double z = clipd(v, lo, hi);
-    roww(w, r) = row_rho(P, pb.E, r, inrm) * (2.0 * z - v);
-  });
-  if (pb.n_obs < 2) {
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-      if (k >= pb.n_obs) {
-#pragma unroll
-        for (int j = 0; j < NH; ++j) { w.o[k][j][0] = 0.0; w.o[k][j][1] = 0.0; }
-      }
-  }
+// One ADMM iteration.
+//   CHECK = false: v += alpha (A x - clip(v)), nothing else.
+//   CHECK = true : additionally residuals, active set, step-size policy; CERT adds the infeasibility certificate.
+template <bool CHECK, bool CERT, int S>
+MPCB_HD void admm_iter(const DevParams& P, Problem& pb, const Store<S>& st, SegStats& stt) {
   double rhs[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) rhs[i] = -pb.q[i];
-  at_mul(P, pb, w, rhs);
-  sym_mul(pb.Kinv, rhs, pb.x);
-  RowW zt;
-  a_mul(P, pb, pb.x, zt);
-  if (!LAST) {
-    for_each_row(P, pb, [&](int r, double& v, double lo, double hi, double inrm) {
+  // pass A: w_r = rho_r (2 clip(v_r) - v_r); the plain iteration folds "- alpha clip(v)" into v on the way
+  {
+    AtAcc<S> acc(P, st, rhs);
+    for_rows(P, pb, st, pb.x, [&](int r, double, double lo, double hi) {
+      const double v = st.v[r];
       const double z = clipd(v, lo, hi);
-      v = fma(P.relax, roww(zt, r) - z, v);
+      acc.add(r, st.rho[r] * fma(2.0, z, -v));
+      if (!CHECK) st.v[r] = fma(-P.relax, z, v);
     });
-  } else {
-    RowW t1, t2;   // t1 = rho (z - zt) + dy ; t2 = dy
-#pragma unroll
-    for (int k = 0; k < 2; ++k)
-#pragma unroll
-      for (int j = 0; j < NH; ++j) { t1.o[k][j][0] = t1.o[k][j][1] = 0.0; t2.o[k][j][0] = t2.o[k][j][1] = 0.0; }
-    double rp = 0.0, nd = 0.0, sup = 0.0, bad = 0.0;
-    unsigned long long act = 0ull;
-    for_each_row(P, pb, [&](int r, double& v, double lo, double hi, double inrm) {
-      const int e = pb.E.get(r);
-      const double rho = P.lad[e] * inrm;
-      const double z = clipd(v, lo, hi);
-      const double ztr = roww(zt, r);
-      const double vn = fma(P.relax, ztr - z, v);
-      const double zn = clipd(vn, lo, hi);
-      const double dy = rho * ((vn - zn) - (v - z));
-      rp = fmax(rp, fabs(ztr - zn));
-      nd = fmax(nd, fabs(dy));
-      if (dy > 0.0) { if (hi < BIG) sup = fma(hi, dy, sup); else bad = fmax(bad, dy); }
-      else if (dy < 0.0) { if (lo > -BIG) sup = fma(lo, dy, sup); else bad = fmax(bad, -dy); }
-      roww(t1, r) = fma(rho, z - ztr, dy);
-      roww(t2, r) = dy;
-      // ladder with hysteresis
-      const bool a_now = (vn < lo) || (vn > hi);
-      const bool a_prev = (pb.act_prev >> r) & 1ull;
-      double vnew = vn;
-      if (a_now && (a_prev || !P.hysteresis) && e < P.n_rung - 1) {
-        const int e2 = (e + P.up_step < P.n_rung - 1) ? e + P.up_step : P.n_rung - 1;
-        pb.E.set(r, e2);
-        vnew = fma(P.lad[e] / P.lad[e2], vn - zn, zn);   // keep (z, y): v' = z + (rho/rho') (v - z)
-      } else if (!a_now && (!a_prev || !P.hysteresis) && e > 0) {
-        pb.E.set(r, P.drop_all ? 0 : e - 1);           // inactive: v == z, nothing to rescale
-      }
-      if (a_now) act |= (1ull << r);
-      v = vnew;
-    });
-    pb.act_prev = act;
-    double o1[NV], o2[NV];
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { o1[i] = 0.0; o2[i] = 0.0; }
-    at_mul(P, pb, t1, o1);
-    at_mul(P, pb, t2, o2);
-    double rd = 0.0, atdy = 0.0;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) { rd = fmax(rd, fabs(o1[i])); atdy = fmax(atdy, fabs(o2[i])); }
-    st.rp = rp; st.rd = rd; st.nd = nd; st.atdy = atdy; st.sup = sup; st.bad = bad;
+    acc.finish();
   }
+  chol_solve(pb, rhs, pb.x);
+  if (!CHECK) {
+    for_rows(P, pb, st, pb.x, [&](int r, double zt, double, double) { st.v[r] = fma(P.relax, zt, st.v[r]); });
+    return;
+  }
+  double o1[NV], o2[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { o1[i] = 0.0; o2[i] = 0.0; }
+  AtAcc<S> acc1(P, st, o1), acc2(P, st, o2);
+  double rp = 0.0, nd = 0.0, sup = 0.0, bad = 0.0;
+  unsigned long long act = 0ull;
+  for_rows(P, pb, st, pb.x, [&](int r, double zt, double lo, double hi) {
+    const double v = st.v[r];
+    const double rho = st.rho[r];
+    const double z = clipd(v, lo, hi);
+    const double vn = fma(P.relax, zt - z, v);
+    const double zn = clipd(vn, lo, hi);
+    rp = dmax(rp, fabs(zt - zn));
+    // dual residual of (x, y_new): A' rho ((2 - alpha) z + (alpha - 1) zt - zn)
+    acc1.add(r, rho * (fma(2.0 - P.relax, z, (P.relax - 1.0) * zt) - zn));
+    if (CERT) {
+      const double dy = rho * ((vn - zn) - (v - z));
+      nd = dmax(nd, fabs(dy));
+      if (dy > 0.0) { if (hi < BIG) sup = fma(hi, dy, sup); else bad = dmax(bad, dy); }
+      else if (dy < 0.0) { if (lo > -BIG) sup = fma(lo, dy, sup); else bad = dmax(bad, -dy); }
+      acc2.add(r, dy);
+    }
+    // step-size policy
+    const int e = pb.E.get(r);
+    const bool a_now = (vn < lo) || (vn > hi);
+    const bool a_prev = (pb.act_prev >> r) & 1ull;
+    double vnew = vn;
+    if (a_now && (a_prev || !P.hysteresis) && e < P.n_rung - 1) {
+      pb.E.set(r, e + 1);
+      vnew = fma(P.lad_ratio[e + 1], vn - zn, zn);   // keep (z, y): v' = z + (rho/rho') (v - z)
+    } else if (!a_now && (!a_prev || !P.hysteresis) && e > 0) {
+      pb.E.set(r, P.drop_all ? 0 : e - 1);           // inactive: v == z, nothing to rescale
+    }
+    if (a_now) act |= (1ull << r);
+    st.v[r] = vnew;
+  });
+  pb.act_prev = act;
+  acc1.finish();
+  double rd = 0.0, atdy = 0.0;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) rd = dmax(rd, fabs(o1[i]));
+  if (CERT) {
+    acc2.finish();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) atdy = dmax(atdy, fabs(o2[i]));
+  }
+  stt.rp = rp; stt.rd = rd; stt.nd = nd; stt.atdy = atdy; stt.sup = sup; stt.bad = bad;
 }
 
 // ------------------------------------------------------------------------------------------------
-// Whole solve for one problem.  Warp-uniform loops (votes) so that divergence only idles lanes.
+// Whole solve for one problem.
 // ------------------------------------------------------------------------------------------------
 struct SolveOut { int status, rounds, iters; bool const_infeasible; };
 
-__device__ __forceinline__ void init_admm_state(const DevParams& P, Problem& pb) {
-  // z = clip(A U), y = 0  ->  v = z ; all rows on the initial rung
+template <bool CERT, int S>
+MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const Store<S>& st, bool live) {
+  SolveOut out{MPCB_MAXITER, 0, 0, false};
+  // Bounds of the rows that are exactly affine in U (speed, obstacle), and a rigorous screen: such a row that
+  // cannot be met anywhere inside the control box makes the problem infeasible whatever the other rows do
+  // (all coefficients are >= 0, so the row's extreme over the box sits at b = u2_min resp. u2_max).  Those rows
+  // are dropped from the QP (the solve then returns the best controls for the remaining rows) and the problem is
+  // flagged infeasible at once instead of waiting for an ADMM certificate.
+  bool screened = false;
 #pragma unroll
-  for (int i = 0; i < 6; ++i) pb.E.w[i] = 0x11111111u * (unsigned)P.e_init;
-  pb.act_prev = 0ull;
-  RowW zt;
-  a_mul(P, pb, pb.U, zt);
-  for_each_row(P, pb, [&](int r, double& v, double lo, double hi, double inrm) { v = clipd(roww(zt, r), lo, hi); });
-}
-
-__device__ __forceinline__ SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, bool live) {
-  // obstacle row offsets
+  for (int j = 0; j < NH; ++j) {
+    const double cmax = P.h * (double)(j + 1) * P.umax[1];            // max of v_{j+1} - v0 over the box
+    const bool dead = cmax < -pb.x0[4] - P.feas_tol;
+    pb.lov[j] = dead ? -BIG : -pb.x0[4];
+    screened |= dead;
+  }
 #pragma unroll
   for (int k = 0; k < 2; ++k)
 #pragma unroll
-    for (int j = 0; j < NH; ++j)
-      pb.base[k][j] = (pb.obs[k][0] + pb.obs[k][1] * ((j + 1) * P.h)) - pb.x0[0] - (j + 1) * P.h * pb.x0[4];
+    for (int j = 1; j <= NH; ++j) {
+      const double base = (pb.obs[k][0] + pb.obs[k][1] * (j * P.h)) - pb.x0[0] - j * P.h * pb.x0[4];
+      const double smin = P.h * P.h * (double)((j - 1) * j / 2) * P.umin[1];     // min of S_j over the box
+      const double cmin = P.h * (double)j * P.umin[1];                           // min of v_j - v0
+      const double h1 = base - P.obs_safe, h2 = base - P.tgap * pb.x0[4];
+      const bool on = k < pb.n_obs;
+      const bool dead1 = on && (smin > h1 + P.feas_tol);           // j = 1: S_1 == 0, the row is constant in U
+      const bool dead2 = on && (smin + P.tgap * cmin > h2 + P.feas_tol);
+      if (j > 1) st.hio[N_OBSROW * k + (j - 2)] = (!on || dead1) ? BIG : h1;
+      st.hio[N_OBSROW * k + 4 + (j - 1)] = (!on || dead2) ? BIG : h2;
+      screened |= dead1 | dead2;
+    }
+#pragma unroll
+  for (int j = 0; j <= NH; ++j) pb.hint[j] = 1;
   warm_start(T, P, pb.x0, pb.obs, pb.n_obs, pb.U);
 #pragma unroll
   for (int i = 0; i < NV; ++i) pb.U[i] = clipd(pb.U[i], P.umin[i & 1], P.umax[i & 1]);  // scipy clips x0 to the bounds
 
-  SolveOut out{MPCB_MAXITER, 0, 0, false};
   bool done = !live;
-  bool infeasible = false;
+  bool infeasible = screened;
+  out.const_infeasible = screened;
   bool first = true;
   for (int round = 0; round < P.max_rounds; ++round) {
     if (MPCB_ALL(done)) break;
     if (!done) {
       double cviol;
-      linearise(T, P, pb, cviol);
-      if (first) { init_admm_state(P, pb); first = false; }
+      linearise(T, P, pb, st, cviol);
+      if (first) {
+        // z = clip(A U), y = 0  ->  v = z ; all rows on the initial rung
+#pragma unroll
+        for (int i = 0; i < 6; ++i) pb.E.w[i] = 0x11111111u * (unsigned)P.e_init;
+        pb.act_prev = 0ull;
+        for_rows(P, pb, st, pb.U, [&](int r, double zt, double lo, double hi) { st.v[r] = clipd(zt, lo, hi); });
+#pragma unroll
+        for (int i = 0; i < NV; ++i) pb.x[i] = pb.U[i];
+        first = false;
+      }
       if (cviol > P.feas_tol) { infeasible = true; out.const_infeasible = true; }
       out.rounds++;
     }
@@ -579,32 +592,23 @@ __device__ __forceinline__ SolveOut solve_one(const DevTable& T, const DevParams
     for (int seg = 0; seg < P.max_segments; ++seg) {
       if (MPCB_ALL(conv)) break;
       if (!conv) {
-        factor(P, pb);
-        SegStats st;
-        for (int it = 0; it < P.segment_iters - 1; ++it) admm_iter<false>(P, pb, st);
-        admm_iter<true>(P, pb, st);
+        factor(P, pb, st);
+        SegStats s;
+        for (int it = 0; it < P.segment_iters - 1; ++it) admm_iter<false, false>(P, pb, st, s);
+        admm_iter<true, CERT>(P, pb, st, s);
         out.iters += P.segment_iters;
-#ifdef MPCB_TRACE
-        if (getenv("MPCB_TRACE")) {
-          printf("  r%d s%d rp %.2e rd %.2e nd %.2e act %012llx E", round, seg, st.rp, st.rd, st.nd, pb.act_prev);
-          for (int r = 0; r < M_ROWS; ++r) printf("%d", pb.E.get(r));
-          printf(" x");
-          for (int i = 0; i < NV; ++i) printf(" %.4f", pb.x[i]);
-          printf("\n");
-        }
-#endif
-        if (st.rp <= P.eps_p && st.rd <= P.eps_d) conv = true;
-        else if (P.trust_cert && st.nd > 1e-9 && st.atdy <= P.eps_inf * st.nd && st.sup < -P.eps_inf * st.nd &&
-                 st.bad <= P.eps_inf * st.nd) { conv = true; cert = true; }
+        if (s.rp <= P.eps_p && s.rd <= P.eps_d) conv = true;
+        else if (CERT && s.nd > 1e-9 && s.atdy <= P.eps_inf * s.nd && s.sup < -P.eps_inf * s.nd &&
+                 s.bad <= P.eps_inf * s.nd) { conv = true; cert = true; }
       }
     }
     if (!done) {
       double step = 0.0;
 #pragma unroll
-      for (int i = 0; i < NV; ++i) { step = fmax(step, fabs(pb.x[i] - pb.U[i])); pb.U[i] = pb.x[i]; }
+      for (int i = 0; i < NV; ++i) { step = dmax(step, fabs(pb.x[i] - pb.U[i])); pb.U[i] = pb.x[i]; }
       if (cert) { infeasible = true; done = true; }
       else if (conv && step < P.step_tol) { done = true; out.status = 0; }
-      else if (!conv && !P.trust_cert) done = true;   // first pass: a QP it cannot close goes to the robust pass
+      else if (!conv && !CERT) done = true;   // first pass: a QP it cannot close goes to the robust pass
     }
   }
   if (infeasible) out.status = 2;

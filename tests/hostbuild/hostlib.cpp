@@ -83,7 +83,9 @@ int host_solve_batch(const double* s, const double* y, const double* u, int K, i
       for (int c = 0; c < 5; ++c) pb.x0[c] = x0[5 * b + c];
       for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[4 * b + 2 * k]; pb.obs[k][1] = obs_sv[4 * b + 2 * k + 1]; }
       pb.n_obs = std::min(std::max(n_obs[b], 0), 2);
-      SolveOut so = solve_one(T, P, pb, true);
+      double buf[Store<1>::DOUBLES];
+      Store<1> st(buf);
+      SolveOut so = (pass == 1) ? solve_one<false>(T, P, pb, st, true) : solve_one<true>(T, P, pb, st, true);
       rounds += so.rounds; iters += so.iters;
       if (pass == 1 && so.status == MPCB_MAXITER) continue;
       double X[NH + 1][5];
