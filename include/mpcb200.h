@@ -195,6 +195,9 @@ int mpcb_hs_nodes(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int
 const char* mpcb_strerror(int code);
 const char* mpcb_last_cuda_error(void);
 int mpcb_abi_version(void);
+/* sizeof(mpcb_params) / sizeof(mpcb_planner_params) as compiled into the library: lets a binding check its mirror. */
+unsigned long long mpcb_sizeof_params(void);
+unsigned long long mpcb_sizeof_planner_params(void);
 
 #ifdef __cplusplus
 }

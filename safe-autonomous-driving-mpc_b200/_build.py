@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libmpcb200.so")
+LIB = os.environ.get("MPCB_LIB") or os.path.join(HERE, "libmpcb200.so")   # MPCB_LIB: development variants
 SOURCES = ["mpcb_api.cu", "mpcb_planner.cu"]
 HEADERS = ["mpcb_device.cuh", "mpcb_solver.cuh", "mpcb_planner.cuh", "mpcb_internal.h"]
 
@@ -26,22 +26,23 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, defines=(), out=None):
     """Compile csrc/*.cu -> libmpcb200.so.  Returns the library path."""
-    if not force and not stale():
+    if out is None and not force and not stale():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
            "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-shared", "-Xcompiler", "-fPIC",
-           "-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+           "-o", out or LIB] + ["-D" + d for d in defines] + [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or res.returncode != 0:
         print(res.stdout)
         print(res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libmpcb200.so")
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
-        f.write(res.stderr)
-    return LIB
+    if out is None:
+        with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
+            f.write(res.stderr)
+    return out or LIB
 
 
 if __name__ == "__main__":

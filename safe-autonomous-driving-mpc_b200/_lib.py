@@ -80,6 +80,8 @@ SYMBOLS = {
     "mpcb_strerror": (C.c_char_p, [C.c_int]),
     "mpcb_last_cuda_error": (C.c_char_p, []),
     "mpcb_abi_version": (C.c_int, []),
+    "mpcb_sizeof_params": (C.c_ulonglong, []),
+    "mpcb_sizeof_planner_params": (C.c_ulonglong, []),
 }
 
 _lib = None
@@ -104,6 +106,8 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)   # AttributeError if the ABI is incomplete: fail loudly
         fn.restype = res
         fn.argtypes = args
+    if lib.mpcb_sizeof_params() != C.sizeof(Params) or lib.mpcb_sizeof_planner_params() != C.sizeof(PlannerParams):
+        raise MpcbError("libmpcb200.so and its ctypes mirror disagree on the parameter structs (stale build?)")
     _lib = lib
     return lib
 

@@ -15,9 +15,18 @@
 
 namespace mpcb {
 
-constexpr int SOLVE_THREADS = 64;   // problems per CTA; 70 KB of shared memory per CTA -> 3 CTAs (6 warps) per SM
-using SolveStore = Store<SOLVE_THREADS>;
-constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::DOUBLES * SOLVE_THREADS;
+#ifndef MPCB_SOLVE_THREADS
+#define MPCB_SOLVE_THREADS 64      // problems per CTA
+#endif
+#ifndef MPCB_SOLVE_CTAS
+#define MPCB_SOLVE_CTAS 4          // CTAs per SM the kernel is compiled for
+#endif
+#ifndef MPCB_STORE_LEVEL
+#define MPCB_STORE_LEVEL 0         // how much of the per-thread working set sits in shared memory (mpcb_solver.cuh)
+#endif
+constexpr int SOLVE_THREADS = MPCB_SOLVE_THREADS;
+using SolveStore = Store<(MPCB_STORE_LEVEL > 0 ? SOLVE_THREADS : 1), MPCB_STORE_LEVEL>;
+constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::SHARED * SOLVE_THREADS;
 constexpr int EVAL_THREADS = 128;
 
 // ------------------------------------------------------------------------------------------------
@@ -27,7 +36,7 @@ constexpr int EVAL_THREADS = 128;
 //               are appended to fb_list / fb_count instead of being written out.
 // ------------------------------------------------------------------------------------------------
 template <bool FIRST_PASS>
-__global__ void __launch_bounds__(SOLVE_THREADS, 3)
+__global__ void __launch_bounds__(SOLVE_THREADS, MPCB_SOLVE_CTAS)
 mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
                   const int* __restrict__ idx, const int* __restrict__ n_idx,
                   const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
@@ -53,8 +62,9 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
     pb.n_obs = 0;
   }
   extern __shared__ double solve_smem[];
-  const SolveStore st(solve_smem + threadIdx.x);
-  SolveOut so = solve_one<!FIRST_PASS>(T, P, pb, st, live);
+  double solve_local[SolveStore::LOCAL > 0 ? SolveStore::LOCAL : 1];
+  const SolveStore st(solve_smem + threadIdx.x, solve_local);
+  SolveOut so = solve_one<FIRST_PASS>(T, P, pb, st, live);
   if (!live) return;
   if (FIRST_PASS && so.status == MPCB_MAXITER) {                   // not certified: leave it to the robust pass
     fb_list[atomicAdd(fb_count, 1)] = b;
@@ -167,17 +177,18 @@ mpcb_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
     pb.obs[0][0] = pb.obs[0][1] = pb.obs[1][0] = pb.obs[1][1] = 0.0;
 #pragma unroll
     for (int j = 0; j <= NH; ++j) pb.hint[j] = 1;
-    double buf[Store<1>::DOUBLES];
-    const Store<1> st(buf);
+    typedef Store<1, 0> EvalStore;
+    double buf[EvalStore::LOCAL];
+    const EvalStore st(nullptr, buf);
     double cv;
     linearise(T, P, pb, st, cv);
     // Export what the solver actually consumes: H (55), q (10), D/O rows (80) packed into the
     // 150-double slot:  [0:55) H, [55:65) q, [65:105) D, [105:145) O, [145:150) unused (zero).
     double* o = Jr_out + (size_t)b * 150;
 #pragma unroll
-    for (int i = 0; i < NTRI; ++i) o[i] = pb.H[i];
+    for (int i = 0; i < NTRI; ++i) o[i] = st.H[i];
 #pragma unroll
-    for (int i = 0; i < NV; ++i) o[55 + i] = pb.q[i];
+    for (int i = 0; i < NV; ++i) o[55 + i] = st.q[i];
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -228,7 +239,9 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 extern "C" {
 
-int mpcb_abi_version(void) { return 2; }
+int mpcb_abi_version(void) { return 3; }
+unsigned long long mpcb_sizeof_params(void) { return sizeof(mpcb_params); }
+unsigned long long mpcb_sizeof_planner_params(void) { return sizeof(mpcb_planner_params); }
 
 const char* mpcb_strerror(int code) {
   switch (code) {
@@ -313,10 +326,8 @@ int mpcb_table_knots(mpcb_table_handle t) { return t ? t->K : MPCB_ERR_INVALID; 
 int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int device) {
   if (!out || !p || !t) return MPCB_ERR_INVALID;
   *out = nullptr;
-  DevParams dp, dp_fast;
-  int rc = derive_params(*p, dp, false);
-  if (rc != MPCB_OK) return rc;
-  rc = derive_params(*p, dp_fast, true);
+  DevParams dp;
+  int rc = derive_params(*p, dp);
   if (rc != MPCB_OK) return rc;
   int ndev = 0;
   CK(cudaGetDeviceCount(&ndev));
@@ -334,7 +345,6 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   c->device = device;
   c->params = *p;
   c->dp = dp;
-  c->dp_fast = dp_fast;
   const int K = t->K;
   c->K = K;
   c->Ku = t->Ku;
@@ -390,7 +400,7 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
     int* fb_count = h->fb;
     int* fb_list = h->fb + 1;
     CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
-    mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp_fast, B, nullptr, nullptr, x0, obs_sv, n_obs,
+    mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
                                                            U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
                                                            active_out, fb_list, fb_count);
     CK(cudaGetLastError());

@@ -48,6 +48,17 @@ struct DevTable {
   double last[4];    // X_ref[-1][1:5], returned for s >= s_max
 };
 
+// Step-size policy of the ADMM machinery (mpcb_solver.cuh).
+struct Policy {
+  double lad[MAXRUNG];        // step-size ladder
+  double lad_ratio[MAXRUNG];  // lad[k-1]/lad[k] (k>=1): rescale of (v - z) when a row moves up one rung
+  double relax;               // ADMM over-relaxation alpha
+  int n_rung, e_init;
+  int hysteresis;             // a row changes rung only after two consecutive segments of the same activity
+  int drop_all;               // inactive rows fall to rung 0 at once
+  int max_segments, segment_iters;
+};
+
 struct DevParams {
   double h;
   double umin[2], umax[2];
@@ -56,12 +67,11 @@ struct DevParams {
   double sld;          // lane_width/2 - vehicle_radius - safe_lane_margin
   double alpha_lane[3];// 0, wheelbase/2, wheelbase
   double brake_lookahead, brake_guess;
-  int max_rounds, max_segments, segment_iters;
-  int n_rung, e_init, hysteresis, drop_all, up_step, trust_cert, init_iters, staged;
-  double lad[MAXRUNG]; // step-size ladder rho_lo * fac^k (capped at rho_hi)
-  double lad_ratio[MAXRUNG]; // lad[k-1]/lad[k] (k>=1): rescale of (v - z) when a row moves up one rung
-  double relax;        // ADMM over-relaxation alpha
+  int max_rounds, fast_max_rounds;
+  int max_fail_rounds; // robust pass: give up after this many rounds whose QP did not close
+  Policy pol[2];       // [0] robust ladder, [1] two-level (first pass)
   double eps_p, eps_d, eps_inf, step_tol, feas_tol;
+  double qp_forcing, qp_eps_loose;   // robust pass: QP tolerance of a round = clamp(forcing * previous SQP step, eps, loose)
   double inrm_v[NH], inrm_r1[NH], inrm_r2[NH];  // 1/max(|a|^2, floor) of the constant-coefficient rows
 };
 

@@ -18,8 +18,7 @@ int cuda_fail(cudaError_t e, const char* where);
 struct mpcb_ctx {
   int device;
   mpcb_params params;
-  mpcb::DevParams dp;        // robust (ladder) pass
-  mpcb::DevParams dp_fast;   // first pass
+  mpcb::DevParams dp;
   mpcb::DevTable dt;
   int K, Ku;
   double* d_s = nullptr;

@@ -31,13 +31,16 @@ inline void default_params(mpcb_params* p) {
   p->fast_max_rounds = 6; p->fast_max_segments = 4; p->fast_segment_iters = 2;
 }
 
-// fast = true: constants of the first pass (two-level step sizes: "off" ~ 0 for inactive rows, "on" = a large
-// augmented-Lagrangian weight for active rows, alpha = 1, no infeasibility verdicts); fast = false: the robust
-// ladder policy of the second pass.
-inline int derive_params(const mpcb_params& p, DevParams& d, bool fast = false) {
+// mpcb_params -> constants of the kernels.  pol[0]: robust ladder (x10 per rung with hysteresis, alpha as given,
+// infeasibility certificate trusted); pol[1]: two-level policy of the first pass ("off" ~ 0 for inactive rows, "on" = a
+// large augmented-Lagrangian weight for active rows, alpha = 1).
+inline int derive_params(const mpcb_params& p, DevParams& d) {
   if (p.N != NH) return MPCB_ERR_UNSUPPORTED;
   if (!(p.dt > 0) || p.max_rounds < 1 || p.max_segments < 1 || p.segment_iters < 1) return MPCB_ERR_INVALID;
   if (!(p.rho_lo > 0) || !(p.rho_hi >= p.rho_lo) || !(p.alpha > 0 && p.alpha < 2)) return MPCB_ERR_INVALID;
+  if (!(p.fast_rho_off > 0) || !(p.fast_rho_on > p.fast_rho_off) || p.fast_max_rounds < 1 ||
+      p.fast_max_segments < 1 || p.fast_segment_iters < 1)
+    return MPCB_ERR_INVALID;
   memset(&d, 0, sizeof(d));
   d.h = p.dt;
   for (int i = 0; i < 2; ++i) { d.umin[i] = p.u_min[i]; d.umax[i] = p.u_max[i]; }
@@ -46,68 +49,42 @@ inline int derive_params(const mpcb_params& p, DevParams& d, bool fast = false) 
   d.sld = p.lane_width / 2.0 - p.vehicle_radius - p.safe_lane_margin;   // trajectory_tracking.py:169
   d.alpha_lane[0] = 0.0; d.alpha_lane[1] = p.wheelbase / 2.0; d.alpha_lane[2] = p.wheelbase;
   d.brake_lookahead = p.brake_lookahead; d.brake_guess = p.brake_guess;
-  d.max_rounds = p.max_rounds; d.max_segments = p.max_segments; d.segment_iters = p.segment_iters;
-  double fac = 10.0;
-  d.hysteresis = 1;
-#ifndef __CUDACC__
-  if (getenv("MPCB_FAC")) fac = atof(getenv("MPCB_FAC"));
-  if (getenv("MPCB_HYST")) d.hysteresis = atoi(getenv("MPCB_HYST"));
-#endif
+  d.max_rounds = p.max_rounds; d.fast_max_rounds = p.fast_max_rounds;
+  // robust ladder
+  Policy& r = d.pol[0];
+  const double fac = 10.0;
   int n = 0;
-  double r = p.rho_lo;
+  double rho = p.rho_lo;
   while (n < MAXRUNG) {
-    d.lad[n++] = std::min(r, p.rho_hi);
-    if (r >= p.rho_hi) break;
-    r *= fac;
+    r.lad[n++] = std::min(rho, p.rho_hi);
+    if (rho >= p.rho_hi) break;
+    rho *= fac;
   }
-  d.n_rung = n;
-  d.lad_ratio[0] = 1.0;
-  for (int k = 1; k < n; ++k) d.lad_ratio[k] = d.lad[k - 1] / d.lad[k];
+  r.n_rung = n;
+  r.lad_ratio[0] = 1.0;
+  for (int k = 1; k < n; ++k) r.lad_ratio[k] = r.lad[k - 1] / r.lad[k];
   int best = 0;
   for (int k = 0; k < n; ++k)
-    if (fabs(log(d.lad[k] / p.rho_init)) < fabs(log(d.lad[best] / p.rho_init))) best = k;
-  d.e_init = best;
-#ifndef __CUDACC__
-  if (getenv("MPCB_LAD")) {
-    const char* q = getenv("MPCB_LAD");
-    n = 0;
-    while (*q && n < MAXRUNG) { char* e; d.lad[n++] = strtod(q, &e); q = (*e == ',') ? e + 1 : e; }
-    d.n_rung = n;
-    d.lad_ratio[0] = 1.0;
-    for (int k = 1; k < n; ++k) d.lad_ratio[k] = d.lad[k - 1] / d.lad[k];
-    d.e_init = getenv("MPCB_EINIT") ? atoi(getenv("MPCB_EINIT")) : 1;
-  }
-  d.drop_all = getenv("MPCB_DROP") ? atoi(getenv("MPCB_DROP")) : 0;
-  d.up_step = getenv("MPCB_UP") ? atoi(getenv("MPCB_UP")) : 1;
-#else
-  d.drop_all = 0; d.up_step = 1;
-#endif
-  d.relax = p.alpha;
-  d.trust_cert = 1;
-  d.staged = 0;
-  d.init_iters = p.segment_iters;
-  if (fast) {
-    if (!(p.fast_rho_off > 0) || !(p.fast_rho_on > p.fast_rho_off) || p.fast_max_rounds < 1 ||
-        p.fast_max_segments < 1 || p.fast_segment_iters < 1)
-      return MPCB_ERR_INVALID;
-    d.lad[0] = p.fast_rho_off; d.lad[1] = p.fast_rho_on;
-    d.lad_ratio[0] = 1.0; d.lad_ratio[1] = d.lad[0] / d.lad[1];
-    d.n_rung = 2; d.e_init = 0; d.hysteresis = 0; d.drop_all = 1; d.up_step = 1;
-    d.relax = 1.0;
-    d.trust_cert = 0;
-    d.init_iters = d.segment_iters;
-#ifndef __CUDACC__
-    if (getenv("MPCB_STAGED")) d.staged = atoi(getenv("MPCB_STAGED"));
-    if (getenv("MPCB_INIT_RHO") && atof(getenv("MPCB_INIT_RHO")) > 0) {
-      d.lad[2] = atof(getenv("MPCB_INIT_RHO"));
-      d.e_init = 2;
-      d.init_iters = getenv("MPCB_INIT_ITERS") ? atoi(getenv("MPCB_INIT_ITERS")) : 4;
-    }
-#endif
-    d.max_rounds = p.fast_max_rounds; d.max_segments = p.fast_max_segments; d.segment_iters = p.fast_segment_iters;
-  }
+    if (fabs(log(r.lad[k] / p.rho_init)) < fabs(log(r.lad[best] / p.rho_init))) best = k;
+  r.e_init = best;
+  r.relax = p.alpha;
+  r.hysteresis = 1; r.drop_all = 0;
+  r.max_segments = p.max_segments; r.segment_iters = p.segment_iters;
+  // two-level policy
+  Policy& f = d.pol[1];
+  f.lad[0] = p.fast_rho_off; f.lad[1] = p.fast_rho_on;
+  f.lad_ratio[0] = 1.0; f.lad_ratio[1] = f.lad[0] / f.lad[1];
+  f.n_rung = 2; f.e_init = 0; f.hysteresis = 0; f.drop_all = 1;
+  f.relax = 1.0;
+  f.max_segments = p.fast_max_segments; f.segment_iters = p.fast_segment_iters;
   d.eps_p = p.eps_prim; d.eps_d = p.eps_dual; d.eps_inf = p.eps_infeas;
   d.step_tol = p.step_tol; d.feas_tol = p.feas_tol;
+  d.qp_forcing = 1e-3; d.qp_eps_loose = 1e-4;
+  d.max_fail_rounds = 2;
+#ifndef __CUDACC__
+  if (getenv("MPCB_FORCING")) d.qp_forcing = atof(getenv("MPCB_FORCING"));
+  if (getenv("MPCB_MAXFAIL")) d.max_fail_rounds = atoi(getenv("MPCB_MAXFAIL"));
+#endif
   const double h = p.dt, floor_ = NRM2_FLOOR;
   for (int j = 1; j <= NH; ++j) {
     double nv = 0, n1 = 0, n2 = 0;
@@ -123,6 +100,5 @@ inline int derive_params(const mpcb_params& p, DevParams& d, bool fast = false) 
   }
   return MPCB_OK;
 }
-
 
 }  // namespace mpcb

@@ -55,22 +55,53 @@ typedef volatile double store_t;
 typedef double store_t;
 #endif
 template <int S>
-struct Col {
+struct Col {           // strided, volatile on the GPU: shared memory
   store_t* p;
   MPCB_HD store_t& operator[](int i) const { return p[i * S]; }
 };
+struct LCol {          // thread-private, plain: registers / local memory, placement left to the compiler
+  double* p;
+  MPCB_HD double& operator[](int i) const { return p[i]; }
+};
+template <bool SHARED, int S> struct ColSel { typedef Col<S> type; };
+template <int S> struct ColSel<false, S> { typedef LCol type; };
 
-// strided per-thread store; S = 1 on the host, S = CTA size in shared memory
-template <int S>
+// Per-thread working set.  LEVEL says how much of it sits in the strided (shared-memory) part:
+//   0  nothing (S must be 1: host build, evaluation kernel)
+//   1  row vectors v, rho, obstacle bounds, lane sensitivities D, O                    (140 doubles)
+//   2  + Cholesky factor L, its reciprocal diagonal, q, lane offsets                    (223 doubles)
+//   3  + H, lane row norms, speed-row bounds                                            (291 doubles)
+// the rest lives in a thread-private buffer of LOCAL doubles.
+template <int S, int LEVEL>
 struct Store {
-  static constexpr int DOUBLES = M_ROWS + M_ROWS + 2 * N_OBSROW + 2 * N_DO;
-  Col<S> v;      // [41] ADMM state
-  Col<S> rho;    // [41] step sizes of the current factorisation
-  Col<S> hio;    // [18] upper bounds of the obstacle rows (BIG: row absent or dropped)
-  Col<S> D, O;   // [20] lane sensitivities
-  MPCB_HD explicit Store(double* b)
-      : v{b}, rho{b + M_ROWS * S}, hio{b + 2 * M_ROWS * S}, D{b + (2 * M_ROWS + 2 * N_OBSROW) * S},
-        O{b + (2 * M_ROWS + 2 * N_OBSROW + N_DO) * S} {}
+  typedef typename ColSel<(LEVEL >= 1), S>::type C1;
+  typedef typename ColSel<(LEVEL >= 2), S>::type C2;
+  typedef typename ColSel<(LEVEL >= 3), S>::type C3;
+  static constexpr int N1 = 2 * M_ROWS + 2 * N_OBSROW + 2 * N_DO;     // 140
+  static constexpr int N2 = NTRI + NV + NV + N_LANE;                  // 83
+  static constexpr int N3 = NTRI + N_LANE + NH;                       // 68
+  static constexpr int SHARED = (LEVEL >= 1 ? N1 : 0) + (LEVEL >= 2 ? N2 : 0) + (LEVEL >= 3 ? N3 : 0);
+  static constexpr int LOCAL = N1 + N2 + N3 - SHARED;
+  C1 v;           // [41] ADMM state
+  C1 rho;         // [41] step sizes of the current factorisation
+  C1 hio;         // [18] upper bounds of the obstacle rows (BIG: row absent or dropped)
+  C1 D, O;        // [20] lane sensitivities
+  C2 L;           // [55] factor of K
+  C2 rdiag;       // [10]
+  C2 q;           // [10]
+  C2 lane_c;      // [8]  row value offset: (d_j + alpha o_j)(U) - a.U
+  C3 H;           // [55]
+  C3 lane_inrm;   // [8]
+  C3 lov;         // [5]  lower bound of the speed rows (-BIG when dropped)
+  // sh: this thread's first element of the strided part; lo: thread-private buffer of LOCAL doubles
+  MPCB_HD Store(double* sh, double* lo) {
+    auto take1 = [&](int n) { C1 c; if (LEVEL >= 1) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
+    auto take2 = [&](int n) { C2 c; if (LEVEL >= 2) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
+    auto take3 = [&](int n) { C3 c; if (LEVEL >= 3) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
+    v = take1(M_ROWS); rho = take1(M_ROWS); hio = take1(2 * N_OBSROW); D = take1(N_DO); O = take1(N_DO);
+    L = take2(NTRI); rdiag = take2(NV); q = take2(NV); lane_c = take2(N_LANE);
+    H = take3(NTRI); lane_inrm = take3(N_LANE); lov = take3(NH);
+  }
 };
 
 struct Rungs {  // 4-bit ladder index per row
@@ -87,15 +118,6 @@ struct Problem {
   // SQP state
   double U[NV];
   double x[NV];
-  // QP data of the current round
-  double H[NTRI];
-  double q[NV];
-  double lane_c[N_LANE];      // row value offset: (d_j + alpha o_j)(U) - a.U
-  double lane_inrm[N_LANE];
-  double lov[NH];             // lower bound of the speed rows (-BIG when dropped)
-  // factor of K
-  double L[NTRI];
-  double rdiag[NV];
   // policy state
   Rungs E;
   unsigned long long act_prev;
@@ -120,7 +142,7 @@ MPCB_HD void rank1(double (&H)[NTRI], const double (&a)[NV], double w) {
 }
 
 template <int J>  // residual rows of step J (1..5): accumulate H and g
-MPCB_HD void accumulate_step(const DevParams& P, Problem& pb, double (&g)[NV], const double (&dD)[NV],
+MPCB_HD void accumulate_step(const DevParams& P, double (&H)[NTRI], double (&g)[NV], const double (&dD)[NV],
                              const double (&dO)[NV], const double (&Xj)[5], const double (&val)[4],
                              const double (&slope)[4]) {
   constexpr int L = 2 * (J - 1);  // support of dD, dO, ds_J
@@ -141,8 +163,8 @@ MPCB_HD void accumulate_step(const DevParams& P, Problem& pb, double (&g)[NV], c
   }
   const double rd = Xj[1] - val[0], ro = Xj[2] - val[1], rv = Xj[4] - val[3];
   if (L > 0) {
-    rank1<L>(pb.H, Jd, 2.0 * P.wd);
-    rank1<L>(pb.H, Jo, 2.0 * P.wo);
+    rank1<L>(H, Jd, 2.0 * P.wd);
+    rank1<L>(H, Jo, 2.0 * P.wo);
 #pragma unroll
     for (int c = 0; c < L; ++c) g[c] += 2.0 * (P.wd * rd * Jd[c] + P.wo * ro * Jo[c]);
   }
@@ -151,13 +173,13 @@ MPCB_HD void accumulate_step(const DevParams& P, Problem& pb, double (&g)[NV], c
   for (int i = 0; i < J; ++i) {
     const double wa = 2.0 * P.wv * Jv[2 * i + 1];
 #pragma unroll
-    for (int k = 0; k <= i; ++k) pb.H[tri(2 * i + 1, 2 * k + 1)] = fma(wa, Jv[2 * k + 1], pb.H[tri(2 * i + 1, 2 * k + 1)]);
+    for (int k = 0; k <= i; ++k) H[tri(2 * i + 1, 2 * k + 1)] = fma(wa, Jv[2 * k + 1], H[tri(2 * i + 1, 2 * k + 1)]);
     g[2 * i + 1] += 2.0 * P.wv * rv * Jv[2 * i + 1];
   }
 }
 
-template <int J, int S>  // lane rows of step J (2..5)
-MPCB_HD void lane_rows(const DevParams& P, Problem& pb, const Store<S>& st, const double (&dD)[NV],
+template <int J, class ST>  // lane rows of step J (2..5)
+MPCB_HD void lane_rows(const DevParams& P, Problem& pb, const ST& st, const double (&dD)[NV],
                        const double (&dO)[NV], const double (&Xj)[5]) {
   constexpr int L = 2 * (J - 1);
   constexpr int o = doff(J - 2);
@@ -175,19 +197,20 @@ MPCB_HD void lane_rows(const DevParams& P, Problem& pb, const Store<S>& st, cons
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
     const double al = a ? P.alpha_lane[2] : 0.0;
-    pb.lane_c[2 * (J - 2) + a] = (Xj[1] + al * Xj[2]) - (dU + al * oU);
+    st.lane_c[2 * (J - 2) + a] = (Xj[1] + al * Xj[2]) - (dU + al * oU);
     const double n2 = dd + 2.0 * al * dox + al * al * oo;
-    pb.lane_inrm[2 * (J - 2) + a] = 1.0 / dmax(n2, NRM2_FLOOR);
+    st.lane_inrm[2 * (J - 2) + a] = 1.0 / dmax(n2, NRM2_FLOOR);
   }
 }
 
-template <int S>
-MPCB_HD void linearise(const DevTable& T, const DevParams& P, Problem& pb, const Store<S>& st, double& const_viol) {
+template <class ST>
+MPCB_HD void linearise(const DevTable& T, const DevParams& P, Problem& pb, const ST& st, double& const_viol) {
   const double h = P.h;
+  double H[NTRI];
 #pragma unroll
-  for (int i = 0; i < NTRI; ++i) pb.H[i] = 0.0;
+  for (int i = 0; i < NTRI; ++i) H[i] = 0.0;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) pb.H[tri(i, i)] = 2.0 * P.wu[i & 1];
+  for (int i = 0; i < NV; ++i) H[tri(i, i)] = 2.0 * P.wu[i & 1];
   double g[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) g[i] = 2.0 * P.wu[i & 1] * pb.U[i];
@@ -229,24 +252,24 @@ MPCB_HD void linearise(const DevTable& T, const DevParams& P, Problem& pb, const
   advance(std::integral_constant<int, 0>{});
   // step 1: rows constant in U
   lookup_state_hint(T, X[0], val, slope, pb.hint[1]);
-  accumulate_step<1>(P, pb, g, dD, dO, X, val, slope);
+  accumulate_step<1>(P, H, g, dD, dO, X, val, slope);
   cv = dmax(cv, fabs(X[1]) - P.sld);
   cv = dmax(cv, fabs(X[1] + P.alpha_lane[2] * X[2]) - P.sld);
   advance(std::integral_constant<int, 1>{});
   lookup_state_hint(T, X[0], val, slope, pb.hint[2]);
-  accumulate_step<2>(P, pb, g, dD, dO, X, val, slope);
+  accumulate_step<2>(P, H, g, dD, dO, X, val, slope);
   lane_rows<2>(P, pb, st, dD, dO, X);
   advance(std::integral_constant<int, 2>{});
   lookup_state_hint(T, X[0], val, slope, pb.hint[3]);
-  accumulate_step<3>(P, pb, g, dD, dO, X, val, slope);
+  accumulate_step<3>(P, H, g, dD, dO, X, val, slope);
   lane_rows<3>(P, pb, st, dD, dO, X);
   advance(std::integral_constant<int, 3>{});
   lookup_state_hint(T, X[0], val, slope, pb.hint[4]);
-  accumulate_step<4>(P, pb, g, dD, dO, X, val, slope);
+  accumulate_step<4>(P, H, g, dD, dO, X, val, slope);
   lane_rows<4>(P, pb, st, dD, dO, X);
   advance(std::integral_constant<int, 4>{});
   lookup_state_hint(T, X[0], val, slope, pb.hint[5]);
-  accumulate_step<5>(P, pb, g, dD, dO, X, val, slope);
+  accumulate_step<5>(P, H, g, dD, dO, X, val, slope);
   lane_rows<5>(P, pb, st, dD, dO, X);
 
   // q = g - H U
@@ -254,9 +277,11 @@ MPCB_HD void linearise(const DevTable& T, const DevParams& P, Problem& pb, const
   for (int i = 0; i < NV; ++i) {
     double acc = g[i];
 #pragma unroll
-    for (int j = 0; j < NV; ++j) acc = fma(-pb.H[i >= j ? tri(i, j) : tri(j, i)], pb.U[j], acc);
-    pb.q[i] = acc;
+    for (int j = 0; j < NV; ++j) acc = fma(-H[i >= j ? tri(i, j) : tri(j, i)], pb.U[j], acc);
+    st.q[i] = acc;
   }
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) st.H[i] = H[i];
   const_viol = cv;
 }
 
@@ -264,8 +289,8 @@ MPCB_HD void linearise(const DevTable& T, const DevParams& P, Problem& pb, const
 // Row walk.  f(r, zt_r, lo, hi) is called for every row in index order with the row value zt_r = (A x)_r.
 // Absent obstacles keep their rows (bounds BIG, rho 0 by construction), so the walk has no data-dependent branch.
 // ------------------------------------------------------------------------------------------------
-template <int S, class F>
-MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const Store<S>& st, const double (&x)[NV], F&& f) {
+template <class ST, class F>
+MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const ST& st, const double (&x)[NV], F&& f) {
   const double h = P.h;
 #pragma unroll
   for (int i = 0; i < NV; ++i) f(i, x[i], P.umin[i & 1], P.umax[i & 1]);
@@ -277,9 +302,9 @@ MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const Store<S>& st,
       dj = fma(st.D[doff(jj) + c], x[c], dj);
       oj = fma(st.O[doff(jj) + c], x[c], oj);
     }
-    f(ROW_LANE + 2 * jj, dj, -P.sld - pb.lane_c[2 * jj], P.sld - pb.lane_c[2 * jj]);
-    f(ROW_LANE + 2 * jj + 1, fma(P.alpha_lane[2], oj, dj), -P.sld - pb.lane_c[2 * jj + 1],
-      P.sld - pb.lane_c[2 * jj + 1]);
+    f(ROW_LANE + 2 * jj, dj, -P.sld - st.lane_c[2 * jj], P.sld - st.lane_c[2 * jj]);
+    f(ROW_LANE + 2 * jj + 1, fma(P.alpha_lane[2], oj, dj), -P.sld - st.lane_c[2 * jj + 1],
+      P.sld - st.lane_c[2 * jj + 1]);
   }
   double cum = 0.0, Sj = 0.0;
 #pragma unroll
@@ -287,7 +312,7 @@ MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const Store<S>& st,
     // S_j = h sum_{m<j} (v_m - v0);  cum = v_j - v0
     if (j > 1) Sj = fma(h, cum, Sj);
     cum = fma(h, x[2 * (j - 1) + 1], cum);
-    f(ROW_V + j - 1, cum, pb.lov[j - 1], BIG);
+    f(ROW_V + j - 1, cum, st.lov[j - 1], BIG);
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       if (j > 1) f(row_r1(k, j), Sj, -BIG, st.hio[N_OBSROW * k + (j - 2)]);
@@ -299,14 +324,14 @@ MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const Store<S>& st,
 // out += A' w, fed row by row in the order for_rows walks (no per-row array needs to be kept):
 //   box rows add straight into out; a lane step's two rows are folded into (wD, wO) and applied when the second
 //   one arrives; speed / obstacle rows are folded into per-step sums Tv, Ts and applied by finish().
-template <int S>
+template <class ST>
 struct AtAcc {
   const DevParams& P;
-  const Store<S>& st;
+  const ST& st;
   double (&out)[NV];
   double w0;
   double Tv[NH], Ts[NH];
-  MPCB_HD AtAcc(const DevParams& P_, const Store<S>& st_, double (&out_)[NV]) : P(P_), st(st_), out(out_), w0(0.0) {
+  MPCB_HD AtAcc(const DevParams& P_, const ST& st_, double (&out_)[NV]) : P(P_), st(st_), out(out_), w0(0.0) {
 #pragma unroll
     for (int j = 0; j < NH; ++j) { Tv[j] = 0.0; Ts[j] = 0.0; }
   }
@@ -352,27 +377,27 @@ struct AtAcc {
 // ------------------------------------------------------------------------------------------------
 // rho_r from the rungs, then K = H + A' diag(rho) A = L L'  (packed lower triangle, reciprocal diagonal kept)
 // ------------------------------------------------------------------------------------------------
-template <int S>
-MPCB_HD void factor(const DevParams& P, Problem& pb, const Store<S>& st) {
+template <class ST>
+MPCB_HD void factor(const DevParams& P, const Policy& pl, Problem& pb, const ST& st) {
   const double h = P.h;
   // step sizes of this factorisation
 #pragma unroll
-  for (int i = 0; i < NV; ++i) st.rho[i] = P.lad[pb.E.get(i)];
+  for (int i = 0; i < NV; ++i) st.rho[i] = pl.lad[pb.E.get(i)];
 #pragma unroll
-  for (int r = 0; r < N_LANE; ++r) st.rho[ROW_LANE + r] = P.lad[pb.E.get(ROW_LANE + r)] * pb.lane_inrm[r];
+  for (int r = 0; r < N_LANE; ++r) st.rho[ROW_LANE + r] = pl.lad[pb.E.get(ROW_LANE + r)] * st.lane_inrm[r];
 #pragma unroll
   for (int j = 1; j <= NH; ++j) {
-    st.rho[ROW_V + j - 1] = P.lad[pb.E.get(ROW_V + j - 1)] * P.inrm_v[j - 1];
+    st.rho[ROW_V + j - 1] = pl.lad[pb.E.get(ROW_V + j - 1)] * P.inrm_v[j - 1];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const bool on = k < pb.n_obs;
-      if (j > 1) st.rho[row_r1(k, j)] = on ? P.lad[pb.E.get(row_r1(k, j))] * P.inrm_r1[j - 1] : 0.0;
-      st.rho[row_r2(k, j)] = on ? P.lad[pb.E.get(row_r2(k, j))] * P.inrm_r2[j - 1] : 0.0;
+      if (j > 1) st.rho[row_r1(k, j)] = on ? pl.lad[pb.E.get(row_r1(k, j))] * P.inrm_r1[j - 1] : 0.0;
+      st.rho[row_r2(k, j)] = on ? pl.lad[pb.E.get(row_r2(k, j))] * P.inrm_r2[j - 1] : 0.0;
     }
   }
-  double (&K)[NTRI] = pb.L;
+  double K[NTRI];
 #pragma unroll
-  for (int i = 0; i < NTRI; ++i) K[i] = pb.H[i];
+  for (int i = 0; i < NTRI; ++i) K[i] = st.H[i];
 #pragma unroll
   for (int i = 0; i < NV; ++i) K[tri(i, i)] += st.rho[i];
   // lane rows of step j:  rho0 D D' + rho1 (D + wb O)(D + wb O)' = D (r0 D + r1 O)' + O (r1 D + r2 O)'
@@ -421,7 +446,7 @@ MPCB_HD void factor(const DevParams& P, Problem& pb, const Store<S>& st) {
     for (int k = 0; k < j; ++k) d = fma(-K[tri(j, k)], K[tri(j, k)], d);
     const double rs = rsqrt(d);
     K[tri(j, j)] = d * rs;
-    pb.rdiag[j] = rs;
+    st.rdiag[j] = rs;
 #pragma unroll
     for (int i = j + 1; i < NV; ++i) {
       double s = K[tri(i, j)];
@@ -430,21 +455,24 @@ MPCB_HD void factor(const DevParams& P, Problem& pb, const Store<S>& st) {
       K[tri(i, j)] = s * rs;
     }
   }
+#pragma unroll
+  for (int i = 0; i < NTRI; ++i) st.L[i] = K[i];
 }
 
 // x = K^-1 r through the factor (column-oriented substitutions: independent updates after every pivot)
-MPCB_HD void chol_solve(const Problem& pb, double (&r)[NV], double (&x)[NV]) {
+template <class ST>
+MPCB_HD void chol_solve(const ST& st, double (&r)[NV], double (&x)[NV]) {
 #pragma unroll
   for (int j = 0; j < NV; ++j) {
-    r[j] *= pb.rdiag[j];
+    r[j] *= st.rdiag[j];
 #pragma unroll
-    for (int i = j + 1; i < NV; ++i) r[i] = fma(-pb.L[tri(i, j)], r[j], r[i]);
+    for (int i = j + 1; i < NV; ++i) r[i] = fma(-st.L[tri(i, j)], r[j], r[i]);
   }
 #pragma unroll
   for (int j = NV - 1; j >= 0; --j) {
-    x[j] = r[j] * pb.rdiag[j];
+    x[j] = r[j] * st.rdiag[j];
 #pragma unroll
-    for (int i = 0; i < j; ++i) r[i] = fma(-pb.L[tri(j, i)], x[j], r[i]);
+    for (int i = 0; i < j; ++i) r[i] = fma(-st.L[tri(j, i)], x[j], r[i]);
   }
 }
 
@@ -453,42 +481,43 @@ struct SegStats { double rp, rd, nd, atdy, sup, bad; };
 // One ADMM iteration.
 //   CHECK = false: v += alpha (A x - clip(v)), nothing else.
 //   CHECK = true : additionally residuals, active set, step-size policy; CERT adds the infeasibility certificate.
-template <bool CHECK, bool CERT, int S>
-MPCB_HD void admm_iter(const DevParams& P, Problem& pb, const Store<S>& st, SegStats& stt) {
+template <bool CHECK, bool CERT, class ST>
+MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const ST& st, SegStats& stt) {
+  const double relax = pl.relax;
   double rhs[NV];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) rhs[i] = -pb.q[i];
+  for (int i = 0; i < NV; ++i) rhs[i] = -st.q[i];
   // pass A: w_r = rho_r (2 clip(v_r) - v_r); the plain iteration folds "- alpha clip(v)" into v on the way
   {
-    AtAcc<S> acc(P, st, rhs);
+    AtAcc<ST> acc(P, st, rhs);
     for_rows(P, pb, st, pb.x, [&](int r, double, double lo, double hi) {
       const double v = st.v[r];
       const double z = clipd(v, lo, hi);
       acc.add(r, st.rho[r] * fma(2.0, z, -v));
-      if (!CHECK) st.v[r] = fma(-P.relax, z, v);
+      if (!CHECK) st.v[r] = fma(-relax, z, v);
     });
     acc.finish();
   }
-  chol_solve(pb, rhs, pb.x);
+  chol_solve(st, rhs, pb.x);
   if (!CHECK) {
-    for_rows(P, pb, st, pb.x, [&](int r, double zt, double, double) { st.v[r] = fma(P.relax, zt, st.v[r]); });
+    for_rows(P, pb, st, pb.x, [&](int r, double zt, double, double) { st.v[r] = fma(relax, zt, st.v[r]); });
     return;
   }
   double o1[NV], o2[NV];
 #pragma unroll
   for (int i = 0; i < NV; ++i) { o1[i] = 0.0; o2[i] = 0.0; }
-  AtAcc<S> acc1(P, st, o1), acc2(P, st, o2);
+  AtAcc<ST> acc1(P, st, o1), acc2(P, st, o2);
   double rp = 0.0, nd = 0.0, sup = 0.0, bad = 0.0;
   unsigned long long act = 0ull;
   for_rows(P, pb, st, pb.x, [&](int r, double zt, double lo, double hi) {
     const double v = st.v[r];
     const double rho = st.rho[r];
     const double z = clipd(v, lo, hi);
-    const double vn = fma(P.relax, zt - z, v);
+    const double vn = fma(relax, zt - z, v);
     const double zn = clipd(vn, lo, hi);
     rp = dmax(rp, fabs(zt - zn));
     // dual residual of (x, y_new): A' rho ((2 - alpha) z + (alpha - 1) zt - zn)
-    acc1.add(r, rho * (fma(2.0 - P.relax, z, (P.relax - 1.0) * zt) - zn));
+    acc1.add(r, rho * (fma(2.0 - relax, z, (relax - 1.0) * zt) - zn));
     if (CERT) {
       const double dy = rho * ((vn - zn) - (v - z));
       nd = dmax(nd, fabs(dy));
@@ -501,11 +530,11 @@ MPCB_HD void admm_iter(const DevParams& P, Problem& pb, const Store<S>& st, SegS
     const bool a_now = (vn < lo) || (vn > hi);
     const bool a_prev = (pb.act_prev >> r) & 1ull;
     double vnew = vn;
-    if (a_now && (a_prev || !P.hysteresis) && e < P.n_rung - 1) {
+    if (a_now && (a_prev || !pl.hysteresis) && e < pl.n_rung - 1) {
       pb.E.set(r, e + 1);
-      vnew = fma(P.lad_ratio[e + 1], vn - zn, zn);   // keep (z, y): v' = z + (rho/rho') (v - z)
-    } else if (!a_now && (!a_prev || !P.hysteresis) && e > 0) {
-      pb.E.set(r, P.drop_all ? 0 : e - 1);           // inactive: v == z, nothing to rescale
+      vnew = fma(pl.lad_ratio[e + 1], vn - zn, zn);   // keep (z, y): v' = z + (rho/rho') (v - z)
+    } else if (!a_now && (!a_prev || !pl.hysteresis) && e > 0) {
+      pb.E.set(r, pl.drop_all ? 0 : e - 1);           // inactive: v == z, nothing to rescale
     }
     if (a_now) act |= (1ull << r);
     st.v[r] = vnew;
@@ -528,8 +557,12 @@ MPCB_HD void admm_iter(const DevParams& P, Problem& pb, const Store<S>& st, SegS
 // ------------------------------------------------------------------------------------------------
 struct SolveOut { int status, rounds, iters; bool const_infeasible; };
 
-template <bool CERT, int S>
-MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const Store<S>& st, bool live) {
+// FIRST_PASS = true : two-level policy only; a QP it cannot close ends the attempt (status MPCB_MAXITER = "not
+//                      certified"), no infeasibility verdict other than the rigorous screens.
+// FIRST_PASS = false: robust ladder with OSQP's infeasibility certificate; inexact Gauss-Newton: the QP of a round is
+//                      solved only as accurately as the previous SQP step warrants (P.qp_forcing).
+template <bool FIRST_PASS, class ST>
+MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const ST& st, bool live) {
   SolveOut out{MPCB_MAXITER, 0, 0, false};
   // Bounds of the rows that are exactly affine in U (speed, obstacle), and a rigorous screen: such a row that
   // cannot be met anywhere inside the control box makes the problem infeasible whatever the other rows do
@@ -541,7 +574,7 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
   for (int j = 0; j < NH; ++j) {
     const double cmax = P.h * (double)(j + 1) * P.umax[1];            // max of v_{j+1} - v0 over the box
     const bool dead = cmax < -pb.x0[4] - P.feas_tol;
-    pb.lov[j] = dead ? -BIG : -pb.x0[4];
+    st.lov[j] = dead ? -BIG : -pb.x0[4];
     screened |= dead;
   }
 #pragma unroll
@@ -569,17 +602,24 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
   bool infeasible = screened;
   out.const_infeasible = screened;
   bool first = true;
-  for (int round = 0; round < P.max_rounds; ++round) {
+  const Policy& pl = P.pol[FIRST_PASS ? 1 : 0];
+  double step_prev = 1e30;
+  int fails = 0;
+  const int max_rounds = FIRST_PASS ? P.fast_max_rounds : P.max_rounds;
+  // cold ADMM state at x: z = clip(A x), y = 0  ->  v = z ; all rows on the initial rung of policy m
+  auto cold_start = [&](const double (&xx)[NV]) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) pb.E.w[i] = 0x11111111u * (unsigned)pl.e_init;
+    pb.act_prev = 0ull;
+    for_rows(P, pb, st, xx, [&](int r, double zt, double lo, double hi) { st.v[r] = clipd(zt, lo, hi); });
+  };
+  for (int round = 0; round < max_rounds; ++round) {
     if (MPCB_ALL(done)) break;
     if (!done) {
       double cviol;
       linearise(T, P, pb, st, cviol);
       if (first) {
-        // z = clip(A U), y = 0  ->  v = z ; all rows on the initial rung
-#pragma unroll
-        for (int i = 0; i < 6; ++i) pb.E.w[i] = 0x11111111u * (unsigned)P.e_init;
-        pb.act_prev = 0ull;
-        for_rows(P, pb, st, pb.U, [&](int r, double zt, double lo, double hi) { st.v[r] = clipd(zt, lo, hi); });
+        cold_start(pb.U);
 #pragma unroll
         for (int i = 0; i < NV; ++i) pb.x[i] = pb.U[i];
         first = false;
@@ -587,28 +627,45 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
       if (cviol > P.feas_tol) { infeasible = true; out.const_infeasible = true; }
       out.rounds++;
     }
-    bool conv = done;
+    // inexact Gauss-Newton: a round's QP is only solved as accurately as the previous SQP step warrants
+    const double loosen = (FIRST_PASS || P.qp_forcing <= 0.0) ? 1.0
+                          : dmax(1.0, (step_prev * P.qp_forcing < P.qp_eps_loose ? step_prev * P.qp_forcing : P.qp_eps_loose) / P.eps_p);
+    const double eps_p = P.eps_p * loosen, eps_d = P.eps_d * loosen;
+    bool conv = false;                           // this round's QP closed
+    bool qdone = done;                           // nothing more to do on this round's QP (closed, certified or caps hit)
     bool cert = false;
-    for (int seg = 0; seg < P.max_segments; ++seg) {
-      if (MPCB_ALL(conv)) break;
-      if (!conv) {
-        factor(P, pb, st);
+    for (int seg = 0; seg < pl.max_segments; ++seg) {
+      if (MPCB_ALL(qdone)) break;
+      if (!qdone) {
+        factor(P, pl, pb, st);
         SegStats s;
-        for (int it = 0; it < P.segment_iters - 1; ++it) admm_iter<false, false>(P, pb, st, s);
-        admm_iter<true, CERT>(P, pb, st, s);
-        out.iters += P.segment_iters;
-        if (s.rp <= P.eps_p && s.rd <= P.eps_d) conv = true;
-        else if (CERT && s.nd > 1e-9 && s.atdy <= P.eps_inf * s.nd && s.sup < -P.eps_inf * s.nd &&
-                 s.bad <= P.eps_inf * s.nd) { conv = true; cert = true; }
+        for (int it = 0; it < pl.segment_iters - 1; ++it) admm_iter<false, false>(P, pl, pb, st, s);
+        admm_iter<true, !FIRST_PASS>(P, pl, pb, st, s);
+        out.iters += pl.segment_iters;
+#ifdef MPCB_TRACE
+        if (getenv("MPCB_TRACE")) {
+          printf("  r%d s%d pass %d rp %.2e rd %.2e nd %.2e act %011llx E", round, seg, FIRST_PASS ? 1 : 2, s.rp, s.rd, s.nd, pb.act_prev);
+          for (int r = 0; r < M_ROWS; ++r) printf("%d", pb.E.get(r));
+          printf(" x");
+          for (int i = 0; i < NV; ++i) printf(" %.4f", pb.x[i]);
+          printf("\n");
+        }
+#endif
+        if (s.rp <= eps_p && s.rd <= eps_d) { conv = true; qdone = true; }
+        else if (!FIRST_PASS && s.nd > 1e-9 && s.atdy <= P.eps_inf * s.nd && s.sup < -P.eps_inf * s.nd &&
+                 s.bad <= P.eps_inf * s.nd) { conv = true; cert = true; qdone = true; }
       }
     }
     if (!done) {
       double step = 0.0;
 #pragma unroll
       for (int i = 0; i < NV; ++i) { step = dmax(step, fabs(pb.x[i] - pb.U[i])); pb.U[i] = pb.x[i]; }
+      step_prev = step;
       if (cert) { infeasible = true; done = true; }
       else if (conv && step < P.step_tol) { done = true; out.status = 0; }
-      else if (!conv && !CERT) done = true;   // first pass: a QP it cannot close goes to the robust pass
+      else if (!conv && FIRST_PASS) done = true;   // first pass: a QP it cannot close goes to the robust pass
+      else if (!conv && ++fails >= P.max_fail_rounds) done = true;   // robust pass: QPs that never close (status 1, or
+                                                                      // 2 through the final constraint check)
     }
   }
   if (infeasible) out.status = 2;

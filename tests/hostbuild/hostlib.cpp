@@ -70,22 +70,20 @@ int host_solve_batch(const double* s, const double* y, const double* u, int K, i
   DevTable T = make_table(s, y, u, K, Ku, s_max, last4);
   mpcb_params pp;
   if (p) pp = *p; else default_params(&pp);
-  DevParams Pr, Pf;
-  int rc = derive_params(pp, Pr, false);
-  if (rc != 0) return rc;
-  rc = derive_params(pp, Pf, true);
+  DevParams P;
+  int rc = derive_params(pp, P);
   if (rc != 0) return rc;
   for (int b = 0; b < B; ++b) {
     int rounds = 0, iters = 0;
     for (int pass = pp.fast_pass ? 1 : 2; pass <= 2; ++pass) {
-      const DevParams& P = (pass == 1) ? Pf : Pr;
       Problem pb;
       for (int c = 0; c < 5; ++c) pb.x0[c] = x0[5 * b + c];
       for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[4 * b + 2 * k]; pb.obs[k][1] = obs_sv[4 * b + 2 * k + 1]; }
       pb.n_obs = std::min(std::max(n_obs[b], 0), 2);
-      double buf[Store<1>::DOUBLES];
-      Store<1> st(buf);
-      SolveOut so = (pass == 1) ? solve_one<false>(T, P, pb, st, true) : solve_one<true>(T, P, pb, st, true);
+      typedef Store<1, 0> HostStore;
+      double buf[HostStore::LOCAL];
+      HostStore st(nullptr, buf);
+      SolveOut so = (pass == 1) ? solve_one<true>(T, P, pb, st, true) : solve_one<false>(T, P, pb, st, true);
       rounds += so.rounds; iters += so.iters;
       if (pass == 1 && so.status == MPCB_MAXITER) continue;
       double X[NH + 1][5];

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mpcb200.h but not exported"
         assert n in _lib.SYMBOLS, f"{n} has no ctypes signature"
-    assert lib.mpcb_abi_version() == 2
+    assert lib.mpcb_abi_version() == 3
     assert lib.mpcb_strerror(-1) == b"invalid argument"
 
 
@@ -39,7 +39,9 @@ def test_params_struct_mirrors_reference_constants():
     assert (p.obstacle_safety_distance, p.max_time_2_obs, p.wheelbase, p.lane_width) == (5.0, 1.5, 2.8, 3.0)
     assert (p.vehicle_radius, p.safe_lane_margin) == (1.0, 0.1)
     # sizeof must match the C struct (catches field drift between header and ctypes)
-    assert C.sizeof(p) == 8 * 18 + 4 * 4 + 8 * 9 + 8  # doubles, ints (+pad), doubles; see header order
+    # sizeof must match the C struct (catches field drift between header and ctypes)
+    assert C.sizeof(p) == _lib.load().mpcb_sizeof_params()
+    assert C.sizeof(_lib.PlannerParams()) == _lib.load().mpcb_sizeof_planner_params()
     
 
 @pytest.mark.parametrize("i", [1, 2, 3])

@@ -1,0 +1,48 @@
+"""Development: build kernel-configuration variants of libmpcb200.so (build/variants/, git-ignored) and time them.
+    python tools/variants.py build            (here, no GPU)
+    python tools/variants.py run              (on the GPU box: one subprocess per variant)"""
+import os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "build", "variants")
+VARIANTS = {
+    "T64_C3_L1": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=1"],
+    "T64_C2_L2": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_LEVEL=2"],
+    "T64_C4_L0": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_LEVEL=0"],
+    "T128_C2_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_LEVEL=0"],
+    "T256_C1_L0": ["MPCB_SOLVE_THREADS=256", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_LEVEL=0"],
+    "T192_C1_L0": ["MPCB_SOLVE_THREADS=192", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_LEVEL=0"],
+    "T128_C1_L1": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_LEVEL=1"],
+    "T128_C3_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=0"],
+    "T128_C4_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_LEVEL=0"],
+    "T256_C2_L0": ["MPCB_SOLVE_THREADS=256", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_LEVEL=0"],
+    "T128_C6_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=6", "MPCB_STORE_LEVEL=0"],
+    "T32_C6_L1": ["MPCB_SOLVE_THREADS=32", "MPCB_SOLVE_CTAS=6", "MPCB_STORE_LEVEL=1"],
+    "T32_C3_L3": ["MPCB_SOLVE_THREADS=32", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=3"],
+    "T32_C4_L2": ["MPCB_SOLVE_THREADS=32", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=2"],
+}
+if sys.argv[1] == "build":
+    import importlib
+    b = importlib.import_module("safe_autonomous_driving_mpc_b200._build")
+    os.makedirs(OUT, exist_ok=True)
+    names = sys.argv[2:] or list(VARIANTS)
+    for n in names:
+        lib = os.path.join(OUT, n + ".so")
+        res = subprocess.run([b.nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+                              "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", b.CSRC, "-shared", "-Xcompiler",
+                              "-fPIC", "-o", lib] + ["-D" + d for d in VARIANTS[n]] +
+                             [os.path.join(b.CSRC, s) for s in b.SOURCES], capture_output=True, text=True)
+        info = [l for l in res.stderr.splitlines() if "solve_kernel" in l or "stack frame" in l or "Used" in l]
+        sel = []
+        for i, l in enumerate(info):
+            if "solve_kernel" in l and "Function properties" in l:
+                sel += [info[i + 1].strip(), info[i + 2].strip()]
+        print(n, res.returncode, " | ".join(sel))
+        if res.returncode != 0:
+            print(res.stderr[-2000:])
+else:
+    for n in (sys.argv[2:] or list(VARIANTS)):
+        env = dict(os.environ, MPCB_LIB=os.path.join(OUT, n + ".so"))
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_quick.py")], env=env, capture_output=True, text=True)
+        lines = r.stdout.strip().splitlines()
+        print(n, lines[-1] if lines else r.stderr[-500:])
