@@ -262,13 +262,12 @@ def run_ours(args):
 
     status = res["status"].copy()
     iters = res["iters"].copy()
-    stats = torch.tensor([ms_dev, ms_e2e], dtype=torch.float64, device=dev)
-    hist = torch.tensor(np.bincount(status, minlength=3)[:3].astype(np.int64), device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)      # time = max over ranks
-        dist.all_reduce(hist, op=dist.ReduceOp.SUM)       # NCCL: statistics only
-    ms_dev_max, ms_e2e_max = (float(v) for v in stats.cpu())
-    hist = [int(v) for v in hist.cpu()]
+    # NCCL is used only here, after the timed regions: MAX of the times, SUM of the statistics (no collective on the
+    # solve path)
+    tot = M.sharding.reduce_stats(status, iters, ms_dev, device=dev)
+    tot_e2e = M.sharding.reduce_stats(status, iters, ms_e2e, device=dev)
+    ms_dev_max, ms_e2e_max = tot["ms_max"], tot_e2e["ms_max"]
+    hist = [tot["solved"], tot["maxiter"], tot["infeasible"]]
 
     if rank == 0:
         # single-solve latency through the reference-shaped call (B = 1, host API, includes launch + copies)

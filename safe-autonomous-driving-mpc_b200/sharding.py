@@ -1,0 +1,74 @@
+"""Batch sharding across the GPUs of one box.
+
+Problems are independent, so the solve path has no collective: rank g of G solves the contiguous shard
+``[g*B//G, (g+1)*B//G)`` of the batch on its own GPU.  ``torch.distributed`` (NCCL on GPUs, gloo in the CPU tests) is
+used only afterwards, to gather results and to reduce statistics:
+
+    shard_bounds      the partition
+    solve_sharded     scatter-free sharded solve + optional gather of (U, status, obj) to every rank
+    reduce_stats      status histogram / iteration sums (SUM) and timings (MAX) over ranks
+"""
+import numpy as np
+
+
+def shard_bounds(B, rank, world):
+    """Contiguous shard [lo, hi) of a batch of B problems owned by `rank` of `world` (sizes differ by at most 1)."""
+    if world < 1 or not (0 <= rank < world):
+        raise ValueError("bad rank/world")
+    return (B * rank) // world, (B * (rank + 1)) // world
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def reduce_stats(status, iters, ms, group=None, device=None):
+    """status [b] int, iters [b,2] int, ms: float (this rank's time).  Returns dict with the whole-job status
+    histogram (SUM), summed rounds / iterations (SUM), problem count (SUM) and the slowest rank's time (MAX)."""
+    import torch
+    dist = _dist()
+    status = np.asarray(status)
+    iters = np.asarray(iters).reshape(-1, 2)
+    hist = np.bincount(status, minlength=3)[:3]
+    sums = torch.tensor([hist[0], hist[1], hist[2], iters[:, 0].sum(), iters[:, 1].sum(), len(status)],
+                        dtype=torch.int64, device=device)
+    tmax = torch.tensor([float(ms)], dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX, group=group)
+    s = [int(v) for v in sums.cpu()]
+    return dict(solved=s[0], maxiter=s[1], infeasible=s[2], rounds=s[3], iters=s[4], problems=s[5],
+                ms_max=float(tmax.cpu()[0]))
+
+
+def solve_sharded(solve_fn, x0, obs_sv, n_obs, group=None, gather=True, device=None):
+    """Every rank holds the whole batch description (x0 [B,5], obs_sv [B,2,2], n_obs [B], numpy) and solves only its
+    shard with ``solve_fn(x0_shard, obs_shard, n_shard) -> dict(U [b,5,2], status [b], obj [b], iters [b,2])``.
+    With ``gather`` the per-shard U / status / obj are all-gathered so that every rank returns the full arrays;
+    otherwise each rank returns its shard only.  Returns (result dict, (lo, hi))."""
+    import torch
+    dist = _dist()
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    B = len(n_obs)
+    lo, hi = shard_bounds(B, rank, world)
+    r = solve_fn(x0[lo:hi], obs_sv[lo:hi], n_obs[lo:hi])
+    out = dict(U=np.asarray(r["U"]).reshape(hi - lo, 5, 2), status=np.asarray(r["status"]).astype(np.int32),
+               obj=np.asarray(r["obj"], dtype=np.float64), iters=np.asarray(r["iters"]).reshape(hi - lo, 2))
+    if not gather or world == 1:
+        return out, (lo, hi)
+    full = {}
+    sizes = [shard_bounds(B, g, world) for g in range(world)]
+    pad = max(h - l for l, h in sizes)
+    for key, width, dt in (("U", 10, torch.float64), ("status", 1, torch.int32), ("obj", 1, torch.float64),
+                           ("iters", 2, torch.int32)):
+        mine = torch.zeros((pad, width), dtype=dt, device=device)
+        mine[: hi - lo] = torch.from_numpy(np.ascontiguousarray(out[key]).reshape(hi - lo, width)).to(device=device, dtype=dt)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)                # results only: never on the solve path
+        cat = torch.cat([p[: h - l] for p, (l, h) in zip(parts, sizes)]).cpu().numpy()
+        full[key] = cat
+    return dict(U=full["U"].reshape(B, 5, 2), status=full["status"].reshape(B), obj=full["obj"].reshape(B),
+                iters=full["iters"].reshape(B, 2)), (lo, hi)

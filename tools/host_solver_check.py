@@ -18,6 +18,7 @@ vp = lambda a: a.ctypes.data_as(C.c_void_p)   # noqa: E731
 
 
 def host_solve(tab, x0, obs, n, params=None):
+    global LAST_PASS
     B = len(n)
     s = np.ascontiguousarray(tab.s)
     y = np.ascontiguousarray(tab.X[:, 1:5])
@@ -27,7 +28,6 @@ def host_solve(tab, x0, obs, n, params=None):
     obs = np.ascontiguousarray(obs, dtype=np.float64)
     n = np.ascontiguousarray(n, dtype=np.int32)
     U = np.zeros((B, 10)); st = np.zeros(B, np.int32); it = np.zeros((B, 2), np.int32); obj = np.zeros(B)
-    global LAST_PASS
     LAST_PASS = np.zeros(B, np.int32)
     rc = lib.host_solve_batch(vp(s), vp(y), vp(u), C.c_int(tab.K), C.c_int(tab.Ku), C.c_double(tab.s_max), vp(last4),
                               params, C.c_int(B), vp(x0), vp(obs), vp(n), vp(U), vp(st), vp(it), vp(obj), vp(LAST_PASS))
