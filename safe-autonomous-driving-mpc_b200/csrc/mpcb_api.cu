@@ -16,10 +16,10 @@
 namespace mpcb {
 
 #ifndef MPCB_SOLVE_THREADS
-#define MPCB_SOLVE_THREADS 64      // problems per CTA
+#define MPCB_SOLVE_THREADS 128     // problems per CTA of the first pass
 #endif
 #ifndef MPCB_SOLVE_CTAS
-#define MPCB_SOLVE_CTAS 4          // CTAs per SM the kernel is compiled for
+#define MPCB_SOLVE_CTAS 2          // CTAs per SM the kernel is compiled for
 #endif
 #ifndef MPCB_STORE_LEVEL
 #define MPCB_STORE_LEVEL 0         // how much of the per-thread working set sits in shared memory (mpcb_solver.cuh)
@@ -360,6 +360,11 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev_mid)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
+  c->xs[0] = c->stream;
+  for (int k = 1; k < 4; ++k) {
+    if ((e = cudaStreamCreateWithFlags(&c->xs[k], cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate"));
+    if ((e = cudaEventCreateWithFlags(&c->xe[k], cudaEventDisableTiming)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
+  }
   c->dt.s = c->d_s; c->dt.y = c->d_y; c->dt.u = c->d_u;
   c->dt.K = K; c->dt.Ku = c->Ku; c->dt.s_max = t->s_max;
   for (int k = 0; k < 4; ++k) c->dt.last[k] = t->last_row[1 + k];
@@ -378,49 +383,67 @@ int mpcb_destroy(mpcb_handle h) {
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_mid) cudaEventDestroy(h->ev_mid);
+  for (int k = 1; k < 4; ++k) {
+    if (h->xs[k]) cudaStreamDestroy(h->xs[k]);
+    if (h->xe[k]) cudaEventDestroy(h->xe[k]);
+  }
+  if (h->pin) cudaFreeHost(h->pin);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return MPCB_OK;
 }
 
 // ---- solve ---------------------------------------------------------------------------------------
+// fallback-list storage for a batch of B problems split into up to HOST_CHUNKS independently launched parts
+static const int HOST_CHUNKS = 4;
+static int ensure_fb(mpcb_handle h, int B) {
+  if (!h->params.fast_pass || B + HOST_CHUNKS <= h->fb_cap) return MPCB_OK;
+  if (h->fb) { CK(cudaFree(h->fb)); h->fb = nullptr; h->fb_cap = 0; }
+  if (cudaMalloc(&h->fb, sizeof(int) * ((size_t)B + HOST_CHUNKS)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
+  h->fb_cap = B + HOST_CHUNKS;
+  return MPCB_OK;
+}
+
+// Enqueue the solve of B problems on `st`.  fb = [count, idx[B]] (device ints) for the two-pass scheme.
+// timed: bracket the passes with the handle's events (single-stream callers only).
 static int launch_solve(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs, double* U_out,
                         double* Xpred_out, double* obj_out, int* status_out, int* iters_out, double* cmin_out,
-                        unsigned long long* active_out, cudaStream_t st) {
+                        unsigned long long* active_out, cudaStream_t st, int* fb, bool timed) {
   const int grid = (B + SOLVE_THREADS - 1) / SOLVE_THREADS;
-  if (h->params.fast_pass && B > h->fb_cap) {        // fallback list: [count, idx[B]]
-    if (h->fb) { CK(cudaFree(h->fb)); h->fb = nullptr; h->fb_cap = 0; }
-    if (cudaMalloc(&h->fb, sizeof(int) * ((size_t)B + 1)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
-    h->fb_cap = B;
-  }
   CK(cudaFuncSetAttribute(mpcb_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
   CK(cudaFuncSetAttribute(mpcb_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
-  CK(cudaEventRecord(h->ev0, st));
+  if (timed) CK(cudaEventRecord(h->ev0, st));
   if (h->params.fast_pass) {
-    int* fb_count = h->fb;
-    int* fb_list = h->fb + 1;
+    int* fb_count = fb;
+    int* fb_list = fb + 1;
     CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
     mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
-                                                           U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
-                                                           active_out, fb_list, fb_count);
+                                                                    U_out, Xpred_out, obj_out, status_out, iters_out,
+                                                                    cmin_out, active_out, fb_list, fb_count);
     CK(cudaGetLastError());
-    CK(cudaEventRecord(h->ev_mid, st));
+    if (timed) CK(cudaEventRecord(h->ev_mid, st));
     // second pass over whatever the first did not certify; CTAs beyond the list length exit at once
-    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs,
-                                                            U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
-                                                            active_out, nullptr, nullptr);
+    // (one warp per CTA when the working set is thread-local: the few leftover warps then never wait for each other)
+    const int t2 = (MPCB_STORE_LEVEL == 0) ? 32 : SOLVE_THREADS;
+    mpcb_solve_kernel<false><<<(B + t2 - 1) / t2, t2, SOLVE_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv,
+                                                                       n_obs, U_out, Xpred_out, obj_out, status_out,
+                                                                       iters_out, cmin_out, active_out, nullptr, nullptr);
     CK(cudaGetLastError());
     h->launches += 2;
   } else {
-    CK(cudaEventRecord(h->ev_mid, st));
+    if (timed) CK(cudaEventRecord(h->ev_mid, st));
     mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
-                                                            U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
-                                                            active_out, nullptr, nullptr);
+                                                                     U_out, Xpred_out, obj_out, status_out, iters_out,
+                                                                     cmin_out, active_out, nullptr, nullptr);
     CK(cudaGetLastError());
     h->launches++;
   }
-  CK(cudaEventRecord(h->ev1, st));
-  h->timed = true;
+  if (timed) {
+    CK(cudaEventRecord(h->ev1, st));
+    h->timed = true;
+    h->pass_timed = true;
+    h->fb_last = fb;
+  }
   return MPCB_OK;
 }
 
@@ -430,11 +453,20 @@ int mpcb_solve_batch(mpcb_handle h, int B, const double* x0, const double* obs_s
   if (!h || B < 0 || (B > 0 && (!x0 || !obs_sv || !n_obs || !U_out))) return MPCB_ERR_INVALID;
   if (B == 0) return MPCB_OK;
   CK(cudaSetDevice(h->device));
+  int rc = ensure_fb(h, B);
+  if (rc != MPCB_OK) return rc;
   return launch_solve(h, B, x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
-                      (cudaStream_t)cuda_stream);
+                      (cudaStream_t)cuda_stream, h->fb, true);
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+// Host-buffer entry point.  Small batches (the reference's B = 1 call in particular) go through one packed pinned
+// staging block: one H2D copy, the two launches, one D2H copy.  Large batches are cut into HOST_CHUNKS parts on as many
+// streams, each part copying straight from / to the caller's arrays, so that the H2D of one part, the kernels of
+// another and the D2H of a third overlap (PCIe is full duplex) and the latency tails of the parts' robust passes overlap
+// each other.
+static const int HOST_PACKED_MAX = 2048;
 
 int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
                           double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
@@ -443,6 +475,7 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
   if (B == 0) return MPCB_OK;
   CK(cudaSetDevice(h->device));
   const size_t nb = (size_t)B;
+  // one layout for both paths; inputs first, outputs after (each block contiguous)
   const size_t o_x0 = 0, o_obs = o_x0 + al256(nb * 40), o_n = o_obs + al256(nb * 32), o_U = o_n + al256(nb * 4),
                o_X = o_U + al256(nb * 80), o_obj = o_X + al256(nb * 240), o_st = o_obj + al256(nb * 8),
                o_it = o_st + al256(nb * 4), o_cm = o_it + al256(nb * 8), o_ac = o_cm + al256(nb * 8),
@@ -452,25 +485,77 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
     if (cudaMalloc(&h->ws, total) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
     h->ws_bytes = total;
   }
-  char* w = (char*)h->ws;
-  cudaStream_t st = h->stream;
-  CK(cudaMemcpyAsync(w + o_x0, x0, nb * 40, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(w + o_obs, obs_sv, nb * 32, cudaMemcpyHostToDevice, st));
-  CK(cudaMemcpyAsync(w + o_n, n_obs, nb * 4, cudaMemcpyHostToDevice, st));
-  int rc = launch_solve(h, B, (double*)(w + o_x0), (double*)(w + o_obs), (int*)(w + o_n), (double*)(w + o_U),
-                        Xpred_out ? (double*)(w + o_X) : nullptr, obj_out ? (double*)(w + o_obj) : nullptr,
-                        status_out ? (int*)(w + o_st) : nullptr, iters_out ? (int*)(w + o_it) : nullptr,
-                        cmin_out ? (double*)(w + o_cm) : nullptr,
-                        active_out ? (unsigned long long*)(w + o_ac) : nullptr, st);
+  int rc = ensure_fb(h, B);
   if (rc != MPCB_OK) return rc;
-  CK(cudaMemcpyAsync(U_out, w + o_U, nb * 80, cudaMemcpyDeviceToHost, st));
-  if (Xpred_out) CK(cudaMemcpyAsync(Xpred_out, w + o_X, nb * 240, cudaMemcpyDeviceToHost, st));
-  if (obj_out) CK(cudaMemcpyAsync(obj_out, w + o_obj, nb * 8, cudaMemcpyDeviceToHost, st));
-  if (status_out) CK(cudaMemcpyAsync(status_out, w + o_st, nb * 4, cudaMemcpyDeviceToHost, st));
-  if (iters_out) CK(cudaMemcpyAsync(iters_out, w + o_it, nb * 8, cudaMemcpyDeviceToHost, st));
-  if (cmin_out) CK(cudaMemcpyAsync(cmin_out, w + o_cm, nb * 8, cudaMemcpyDeviceToHost, st));
-  if (active_out) CK(cudaMemcpyAsync(active_out, w + o_ac, nb * 8, cudaMemcpyDeviceToHost, st));
-  CK(cudaStreamSynchronize(st));
+  char* w = (char*)h->ws;
+  double* dU = (double*)(w + o_U);
+  double* dX = Xpred_out ? (double*)(w + o_X) : nullptr;
+  double* dobj = obj_out ? (double*)(w + o_obj) : nullptr;
+  int* dst = status_out ? (int*)(w + o_st) : nullptr;
+  int* dit = iters_out ? (int*)(w + o_it) : nullptr;
+  double* dcm = cmin_out ? (double*)(w + o_cm) : nullptr;
+  unsigned long long* dac = active_out ? (unsigned long long*)(w + o_ac) : nullptr;
+
+  if (B <= HOST_PACKED_MAX) {
+    if (total > h->pin_bytes) {
+      if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_bytes = 0; }
+      size_t want = total;
+      { const size_t nmax = HOST_PACKED_MAX; want = std::max(want, (size_t)(al256(nmax * 40) + al256(nmax * 32) + 2 * al256(nmax * 4) + al256(nmax * 80) + al256(nmax * 240) + 4 * al256(nmax * 8))); }
+      if (cudaHostAlloc(&h->pin, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
+      h->pin_bytes = want;
+    }
+    char* p = (char*)h->pin;
+    cudaStream_t st = h->stream;
+    memcpy(p + o_x0, x0, nb * 40);
+    memcpy(p + o_obs, obs_sv, nb * 32);
+    memcpy(p + o_n, n_obs, nb * 4);
+    CK(cudaMemcpyAsync(w, p, o_U, cudaMemcpyHostToDevice, st));
+    rc = launch_solve(h, B, (double*)(w + o_x0), (double*)(w + o_obs), (int*)(w + o_n), dU, dX, dobj, dst, dit, dcm, dac,
+                      st, h->fb, true);
+    if (rc != MPCB_OK) return rc;
+    CK(cudaMemcpyAsync(p + o_U, w + o_U, total - o_U, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    memcpy(U_out, p + o_U, nb * 80);
+    if (Xpred_out) memcpy(Xpred_out, p + o_X, nb * 240);
+    if (obj_out) memcpy(obj_out, p + o_obj, nb * 8);
+    if (status_out) memcpy(status_out, p + o_st, nb * 4);
+    if (iters_out) memcpy(iters_out, p + o_it, nb * 8);
+    if (cmin_out) memcpy(cmin_out, p + o_cm, nb * 8);
+    if (active_out) memcpy(active_out, p + o_ac, nb * 8);
+    return MPCB_OK;
+  }
+
+  // chunked, one stream per part
+  CK(cudaEventRecord(h->ev0, h->xs[0]));
+  for (int c = 0; c < HOST_CHUNKS; ++c) {
+    const size_t lo = nb * c / HOST_CHUNKS, hi = nb * (c + 1) / HOST_CHUNKS, n = hi - lo;
+    if (n == 0) continue;
+    cudaStream_t st = h->xs[c];
+    if (c > 0) CK(cudaStreamWaitEvent(st, h->ev0, 0));
+    CK(cudaMemcpyAsync(w + o_x0 + lo * 40, x0 + lo * 5, n * 40, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w + o_obs + lo * 32, obs_sv + lo * 4, n * 32, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(w + o_n + lo * 4, n_obs + lo, n * 4, cudaMemcpyHostToDevice, st));
+    rc = launch_solve(h, (int)n, (double*)(w + o_x0) + lo * 5, (double*)(w + o_obs) + lo * 4, (int*)(w + o_n) + lo,
+                      dU + lo * 10, dX ? dX + lo * 30 : nullptr, dobj ? dobj + lo : nullptr, dst ? dst + lo : nullptr,
+                      dit ? dit + lo * 2 : nullptr, dcm ? dcm + lo : nullptr, dac ? dac + lo : nullptr, st,
+                      h->fb + lo + c, false);
+    if (rc != MPCB_OK) return rc;
+    CK(cudaMemcpyAsync(U_out + lo * 10, dU + lo * 10, n * 80, cudaMemcpyDeviceToHost, st));
+    if (Xpred_out) CK(cudaMemcpyAsync(Xpred_out + lo * 30, dX + lo * 30, n * 240, cudaMemcpyDeviceToHost, st));
+    if (obj_out) CK(cudaMemcpyAsync(obj_out + lo, dobj + lo, n * 8, cudaMemcpyDeviceToHost, st));
+    if (status_out) CK(cudaMemcpyAsync(status_out + lo, dst + lo, n * 4, cudaMemcpyDeviceToHost, st));
+    if (iters_out) CK(cudaMemcpyAsync(iters_out + lo * 2, dit + lo * 2, n * 8, cudaMemcpyDeviceToHost, st));
+    if (cmin_out) CK(cudaMemcpyAsync(cmin_out + lo, dcm + lo, n * 8, cudaMemcpyDeviceToHost, st));
+    if (active_out) CK(cudaMemcpyAsync(active_out + lo, dac + lo, n * 8, cudaMemcpyDeviceToHost, st));
+    if (c > 0) {
+      CK(cudaEventRecord(h->xe[c], st));
+      CK(cudaStreamWaitEvent(h->xs[0], h->xe[c], 0));
+    }
+  }
+  CK(cudaEventRecord(h->ev1, h->xs[0]));
+  h->timed = true;           // mpcb_last_kernel_ms: device span of the whole pipeline (copies included)
+  h->pass_timed = false;
+  CK(cudaStreamSynchronize(h->xs[0]));
   return MPCB_OK;
 }
 
@@ -529,7 +614,7 @@ int mpcb_last_kernel_ms(mpcb_handle h, float* ms) {
 }
 
 int mpcb_last_pass_ms(mpcb_handle h, float* first_ms, float* second_ms, int* n_second) {
-  if (!h || !h->timed) return MPCB_ERR_INVALID;
+  if (!h || !h->timed || !h->pass_timed) return MPCB_ERR_INVALID;
   CK(cudaSetDevice(h->device));
   CK(cudaEventSynchronize(h->ev1));
   float a = 0.f, b = 0.f;
@@ -539,7 +624,7 @@ int mpcb_last_pass_ms(mpcb_handle h, float* first_ms, float* second_ms, int* n_s
   if (second_ms) *second_ms = b;
   if (n_second) {
     *n_second = 0;
-    if (h->params.fast_pass && h->fb) CK(cudaMemcpy(n_second, h->fb, sizeof(int), cudaMemcpyDeviceToHost));
+    if (h->params.fast_pass && h->fb_last) CK(cudaMemcpy(n_second, h->fb_last, sizeof(int), cudaMemcpyDeviceToHost));
   }
   return MPCB_OK;
 }

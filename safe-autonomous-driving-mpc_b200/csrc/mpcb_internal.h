@@ -31,6 +31,12 @@ struct mpcb_ctx {
   int fb_cap = 0;
   cudaStream_t stream = nullptr;   // private stream of the *_host entry points
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;
+  cudaStream_t xs[4] = {nullptr, nullptr, nullptr, nullptr};   // xs[0] == stream; one stream per part of a large host batch
+  cudaEvent_t xe[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* pin = nullptr;             // pinned staging block of the packed small-batch path
+  size_t pin_bytes = 0;
+  int* fb_last = nullptr;          // list used by the last timed solve
   bool timed = false;
+  bool pass_timed = false;
   unsigned long long launches = 0;
 };
