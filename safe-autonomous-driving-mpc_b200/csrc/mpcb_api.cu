@@ -12,6 +12,7 @@
 
 #include "mpcb200.h"
 #include "mpcb_solver.cuh"
+#include "mpcb_coop.cuh"
 
 namespace mpcb {
 
@@ -29,43 +30,16 @@ using SolveStore = Store<(MPCB_STORE_LEVEL > 0 ? SOLVE_THREADS : 1), MPCB_STORE_
 constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::SHARED * SOLVE_THREADS;
 constexpr int EVAL_THREADS = 128;
 
-// ------------------------------------------------------------------------------------------------
-// Solve kernel: one thread per problem, CTA-uniform loop control.
-//   work list   idx == nullptr: problems 0..B-1;  else problems idx[0 .. *n_idx - 1] (second pass)
-//   FIRST_PASS  problems this pass cannot certify (iteration caps hit, or a verdict only the robust pass may give)
-//               are appended to fb_list / fb_count instead of being written out.
-// ------------------------------------------------------------------------------------------------
+// Final evaluation at U* (predict, cost, constraint rows in the reference's order), flags, outputs.  In the first pass a
+// problem that is not certified is appended to the work list of the robust pass instead (its iteration counts are
+// still recorded, the robust pass adds its own).
 template <bool FIRST_PASS>
-__global__ void __launch_bounds__(SOLVE_THREADS, MPCB_SOLVE_CTAS)
-mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
-                  const int* __restrict__ idx, const int* __restrict__ n_idx,
-                  const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
-                  double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
-                  int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
-                  unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count) {
-  const int n_work = idx ? min(*n_idx, B) : B;
-  if ((int)(blockIdx.x * blockDim.x) >= n_work) return;          // CTA-uniform
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool live = t < n_work;
-  const int b = live ? (idx ? idx[t] : t) : 0;
-  Problem pb;
-  if (live) {
-#pragma unroll
-    for (int c = 0; c < 5; ++c) pb.x0[c] = x0[(size_t)b * 5 + c];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[(size_t)b * 4 + 2 * k]; pb.obs[k][1] = obs_sv[(size_t)b * 4 + 2 * k + 1]; }
-    pb.n_obs = min(max(n_obs[b], 0), 2);
-  } else {
-#pragma unroll
-    for (int c = 0; c < 5; ++c) pb.x0[c] = 0.0;
-    pb.obs[0][0] = pb.obs[0][1] = pb.obs[1][0] = pb.obs[1][1] = 0.0;
-    pb.n_obs = 0;
-  }
-  extern __shared__ double solve_smem[];
-  double solve_local[SolveStore::LOCAL > 0 ? SolveStore::LOCAL : 1];
-  const SolveStore st(solve_smem + threadIdx.x, solve_local);
-  SolveOut so = solve_one<FIRST_PASS>(T, P, pb, st, live);
-  if (!live) return;
+__device__ __forceinline__ void finalize(const DevTable& T, const DevParams& P, const Problem& pb, const SolveOut& so, int b,
+                                         bool accumulate, double* __restrict__ U_out, double* __restrict__ Xpred_out,
+                                         double* __restrict__ obj_out, int* __restrict__ status_out,
+                                         int* __restrict__ iters_out, double* __restrict__ cmin_out,
+                                         unsigned long long* __restrict__ active_out, int* __restrict__ fb_list,
+                                         int* __restrict__ fb_count) {
   if (FIRST_PASS && so.status == MPCB_MAXITER) {                   // not certified: leave it to the robust pass
     fb_list[atomicAdd(fb_count, 1)] = b;
     if (iters_out) { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
@@ -113,11 +87,85 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
   if (obj_out) obj_out[b] = cost;
   if (status_out) status_out[b] = status;
   if (iters_out) {
-    if (idx) { iters_out[2 * b] += so.rounds; iters_out[2 * b + 1] += so.iters; }     // work of both passes
+    if (accumulate) { iters_out[2 * b] += so.rounds; iters_out[2 * b + 1] += so.iters; }     // work of both passes
     else { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
   }
   if (cmin_out) cmin_out[b] = cmin;
   if (active_out) active_out[b] = act;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Solve kernel: one thread per problem, CTA-uniform loop control.
+//   work list   idx == nullptr: problems 0..B-1;  else problems idx[0 .. *n_idx - 1] (second pass)
+//   FIRST_PASS  problems this pass cannot certify (iteration caps hit, or a verdict only the robust pass may give)
+//               are appended to fb_list / fb_count instead of being written out.
+// ------------------------------------------------------------------------------------------------
+template <bool FIRST_PASS>
+__global__ void __launch_bounds__(SOLVE_THREADS, MPCB_SOLVE_CTAS)
+mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
+                  const int* __restrict__ idx, const int* __restrict__ n_idx,
+                  const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
+                  double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
+                  int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
+                  unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  const int n_work = idx ? min(*n_idx, B) : B;
+  if ((int)(blockIdx.x * blockDim.x) >= n_work) return;          // CTA-uniform
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < n_work;
+  const int b = live ? (idx ? idx[t] : t) : 0;
+  Problem pb;
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) pb.x0[c] = x0[(size_t)b * 5 + c];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[(size_t)b * 4 + 2 * k]; pb.obs[k][1] = obs_sv[(size_t)b * 4 + 2 * k + 1]; }
+    pb.n_obs = min(max(n_obs[b], 0), 2);
+  } else {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) pb.x0[c] = 0.0;
+    pb.obs[0][0] = pb.obs[0][1] = pb.obs[1][0] = pb.obs[1][1] = 0.0;
+    pb.n_obs = 0;
+  }
+  extern __shared__ double solve_smem[];
+  double solve_local[SolveStore::LOCAL > 0 ? SolveStore::LOCAL : 1];
+  const SolveStore st(solve_smem + threadIdx.x, solve_local);
+  SolveOut so = solve_one<FIRST_PASS>(T, P, pb, st, live);
+  if (!live) return;
+  finalize<FIRST_PASS>(T, P, pb, so, b, idx != nullptr, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
+                       active_out, fb_list, fb_count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Warp-per-problem kernel (mpcb_coop.cuh): the robust pass over the work list, and whole small batches.
+// ------------------------------------------------------------------------------------------------
+constexpr int COOP_WARPS = 4;
+
+template <bool FIRST_PASS>
+__global__ void __launch_bounds__(COOP_WARPS * 32)
+mpcb_coop_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
+                 const int* __restrict__ idx, const int* __restrict__ n_idx,
+                 const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
+                 double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
+                 int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
+                 unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  __shared__ WarpShared sh[COOP_WARPS];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  WarpShared& ws = sh[wid];
+  const int n_work = idx ? min(*n_idx, B) : B;
+  const int n_warps = gridDim.x * COOP_WARPS;
+  for (int t = blockIdx.x * COOP_WARPS + wid; t < n_work; t += n_warps) {
+    const int b = idx ? idx[t] : t;
+    __syncwarp();
+    if (lane < 5) ws.pb.x0[lane] = x0[(size_t)b * 5 + lane];
+    if (lane < 4) ws.pb.obs[lane >> 1][lane & 1] = obs_sv[(size_t)b * 4 + lane];
+    if (lane == 0) ws.pb.n_obs = min(max(n_obs[b], 0), 2);
+    __syncwarp();
+    const SolveOut so = coop_solve<FIRST_PASS>(T, P, ws, lane);
+    if (lane == 0)
+      finalize<FIRST_PASS>(T, P, ws.pb, so, b, idx != nullptr, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
+                           active_out, fb_list, fb_count);
+    __syncwarp();
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -343,6 +391,7 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   mpcb_ctx* c = new (std::nothrow) mpcb_ctx();
   if (!c) return MPCB_ERR_NOMEM;
   c->device = device;
+  c->n_sm = prop.multiProcessorCount;
   c->params = *p;
   c->dp = dp;
   const int K = t->K;
@@ -422,12 +471,21 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
                                                                     cmin_out, active_out, fb_list, fb_count);
     CK(cudaGetLastError());
     if (timed) CK(cudaEventRecord(h->ev_mid, st));
-    // second pass over whatever the first did not certify; CTAs beyond the list length exit at once
-    // (one warp per CTA when the working set is thread-local: the few leftover warps then never wait for each other)
-    const int t2 = (MPCB_STORE_LEVEL == 0) ? 32 : SOLVE_THREADS;
-    mpcb_solve_kernel<false><<<(B + t2 - 1) / t2, t2, SOLVE_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv,
-                                                                       n_obs, U_out, Xpred_out, obj_out, status_out,
-                                                                       iters_out, cmin_out, active_out, nullptr, nullptr);
+    // second pass over whatever the first did not certify
+    if (h->params.coop_pass2) {
+      // one warp per problem: the leftovers are few and hard, what matters is their latency
+      const int g2 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * 4);
+      mpcb_coop_kernel<false><<<g2, COOP_WARPS * 32, 0, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs, U_out,
+                                                             Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
+                                                             nullptr, nullptr);
+    } else {
+      // thread per problem; CTAs beyond the list length exit at once (one warp per CTA when the working set is
+      // thread-local: the few leftover warps then never wait for each other)
+      const int t2 = (MPCB_STORE_LEVEL == 0) ? 32 : SOLVE_THREADS;
+      mpcb_solve_kernel<false><<<(B + t2 - 1) / t2, t2, SOLVE_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv,
+                                                                         n_obs, U_out, Xpred_out, obj_out, status_out,
+                                                                         iters_out, cmin_out, active_out, nullptr, nullptr);
+    }
     CK(cudaGetLastError());
     h->launches += 2;
   } else {

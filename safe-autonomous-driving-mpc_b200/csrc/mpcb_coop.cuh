@@ -1,0 +1,305 @@
+// mpcb_coop.cuh -- the same SQP / ADMM algorithm as mpcb_solver.cuh, executed by ONE WARP PER PROBLEM.
+//
+// Why a second execution shape: one thread per problem maximises throughput on a full batch but a single thread walks
+// ~1,400 instructions per ADMM iteration, so the few hard problems of the robust pass (and a B = 1 call) take as long
+// as their serial instruction chain.  Here the 41 rows of the QP are spread over the lanes (lane l owns rows l and
+// l + 32, as dense 10-vectors), the row work of an iteration is 2 rows per lane, A'w is a warp all-reduce of 10
+// partial sums, x = K^-1 rhs is one row of K^-1 per lane (lanes 0..9) followed by a broadcast, and the factorisation
+// is a lane-parallel Cholesky + 10 simultaneous substitutions: ~300 instructions per lane and iteration.
+// Scalar stages that run once per Gauss-Newton round (screen / warm start, linearisation, final evaluation) reuse the
+// thread-level code on lane 0 with a thread-private store placed in shared memory.
+//
+// Everything that decides control flow (residuals, certificate quantities, step) is all-reduced, so the lanes of a warp
+// take the same branches; warps are independent (no CTA barrier).
+#pragma once
+#include "mpcb_solver.cuh"
+
+namespace mpcb {
+
+constexpr int CW_K = 2;                 // rows per lane
+constexpr int CW_ROWS = 32 * CW_K;      // padded row count (rows >= M_ROWS are null)
+
+struct WarpShared {
+  double buf[Store<1, 0>::LOCAL];       // lane 0's thread-level store (H, q, D, O, lane_c, ...)
+  Problem pb;
+  double A[CW_ROWS][NV + 1];            // dense rows (+1 pad: conflict-free column reads)
+  double rho[CW_ROWS];
+  double K[NV][NV + 1];                 // K, then its Cholesky factor (lower)
+  double rdiag[NV];
+  double scal[4];                       // lane-0 scalars broadcast through shared memory
+  int iflag[2];
+};
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// dense coefficients, bounds and 1/|a|^2 of row r at the current linearisation (same rows as for_rows)
+__device__ __forceinline__ void coop_row(const DevParams& P, const Store<1, 0>& st, const Problem& pb, int r,
+                                         double (&a)[NV], double& lo, double& hi, double& inrm, bool& exists) {
+  const double h = P.h;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) a[i] = 0.0;
+  lo = -BIG; hi = BIG; inrm = 0.0; exists = false;
+  if (r < ROW_LANE) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) if (i == r) a[i] = 1.0;
+    lo = P.umin[r & 1]; hi = P.umax[r & 1]; inrm = 1.0; exists = true;
+  } else if (r < ROW_V) {
+    const int q = r - ROW_LANE, jj = q >> 1;
+    const double al = (q & 1) ? P.alpha_lane[2] : 0.0;
+#pragma unroll
+    for (int c = 0; c < NV - 2; ++c)
+      if (c < 2 * (jj + 1)) a[c] = fma(al, st.O[doff(jj) + c], st.D[doff(jj) + c]);
+    lo = -P.sld - st.lane_c[q]; hi = P.sld - st.lane_c[q]; inrm = st.lane_inrm[q]; exists = true;
+  } else if (r < ROW_OBS) {
+    const int j = r - ROW_V + 1;
+#pragma unroll
+    for (int i = 0; i < NH; ++i) if (i < j) a[2 * i + 1] = h;
+    lo = st.lov[j - 1]; inrm = P.inrm_v[j - 1]; exists = true;
+  } else if (r < M_ROWS) {
+    const int q = (r - ROW_OBS) % N_OBSROW, k = (r - ROW_OBS) / N_OBSROW;
+    const bool r2 = q >= 4;
+    const int j = r2 ? q - 3 : q + 2;
+#pragma unroll
+    for (int i = 0; i < NH; ++i) {
+      double c = (i < j - 1) ? h * h * (double)(j - 1 - i) : 0.0;
+      if (r2 && i < j) c += P.tgap * h;
+      a[2 * i + 1] = c;
+    }
+    hi = st.hio[N_OBSROW * k + q];
+    inrm = r2 ? P.inrm_r2[j - 1] : P.inrm_r1[j - 1];
+    exists = k < pb.n_obs;
+  }
+}
+
+template <bool FIRST_PASS>
+__device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared& ws, int lane) {
+  const unsigned FULL = 0xffffffffu;
+  const Store<1, 0> st(nullptr, ws.buf);
+  Problem& pb = ws.pb;
+  const Policy& pl = P.pol[FIRST_PASS ? 1 : 0];
+  SolveOut out{MPCB_MAXITER, 0, 0, false};
+  if (lane == 0) ws.iflag[0] = prologue(T, P, pb, st) ? 1 : 0;
+  __syncwarp();
+  const bool screened = ws.iflag[0] != 0;
+  bool infeasible = screened;
+  out.const_infeasible = screened;
+  bool done = false, first = true;
+  double step_prev = 1e30;
+  int fails = 0;
+  const int max_rounds = FIRST_PASS ? P.fast_max_rounds : P.max_rounds;
+
+  // per-lane row state
+  double a[CW_K][NV], v[CW_K], rho[CW_K], lo[CW_K], hi[CW_K], inrm[CW_K];
+  int e[CW_K];
+  bool ex[CW_K], aprev[CW_K];
+  double x[NV];       // replicated iterate
+  double kinv[NV];    // row `lane` of K^-1 (lanes 0..9)
+#pragma unroll
+  for (int i = 0; i < NV; ++i) { x[i] = 0.0; kinv[i] = 0.0; }
+#pragma unroll
+  for (int k = 0; k < CW_K; ++k) { v[k] = 0.0; rho[k] = 0.0; e[k] = 0; aprev[k] = false; }
+
+  // all-reduced  out[i] = sum_rows a_r[i] t_r
+  auto at_reduce = [&](const double (&t)[CW_K], double (&o)[NV]) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      double p = 0.0;
+#pragma unroll
+      for (int k = 0; k < CW_K; ++k) p = fma(a[k][i], t[k], p);
+      o[i] = warp_sum(p);
+    }
+  };
+
+  for (int round = 0; round < max_rounds && !done; ++round) {
+    if (lane == 0) {
+      double cviol;
+      linearise(T, P, pb, st, cviol);
+      ws.scal[0] = cviol;
+    }
+    __syncwarp();
+    if (ws.scal[0] > P.feas_tol) { infeasible = true; out.const_infeasible = true; }
+    out.rounds++;
+    // dense rows of this round
+#pragma unroll
+    for (int k = 0; k < CW_K; ++k) {
+      const int r = lane + 32 * k;
+      coop_row(P, st, pb, r, a[k], lo[k], hi[k], inrm[k], ex[k]);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) ws.A[r][i] = a[k][i];
+    }
+    if (first) {
+      // cold ADMM state at U: z = clip(A U), y = 0 -> v = z ; all rows on the initial rung
+#pragma unroll
+      for (int i = 0; i < NV; ++i) x[i] = pb.U[i];
+#pragma unroll
+      for (int k = 0; k < CW_K; ++k) {
+        double zt = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) zt = fma(a[k][i], x[i], zt);
+        v[k] = clipd(zt, lo[k], hi[k]);
+        e[k] = pl.e_init;
+        aprev[k] = false;
+      }
+      first = false;
+    }
+    const double loosen = (FIRST_PASS || P.qp_forcing <= 0.0) ? 1.0
+                          : dmax(1.0, (step_prev * P.qp_forcing < P.qp_eps_loose ? step_prev * P.qp_forcing : P.qp_eps_loose) / P.eps_p);
+    const double eps_p = P.eps_p * loosen, eps_d = P.eps_d * loosen;
+    bool conv = false, cert = false;
+    for (int seg = 0; seg < pl.max_segments && !conv; ++seg) {
+      // ---- factor: K = H + A' diag(rho) A, Cholesky, K^-1 rows ------------------------------------------------
+#pragma unroll
+      for (int k = 0; k < CW_K; ++k) {
+        rho[k] = ex[k] ? pl.lad[e[k]] * inrm[k] : 0.0;
+        ws.rho[lane + 32 * k] = rho[k];
+      }
+      __syncwarp();
+      for (int idx = lane; idx < NTRI; idx += 32) {
+        int i = 0;
+        while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+        const int j = idx - i * (i + 1) / 2;
+        double acc = st.H[idx];
+        for (int r = 0; r < M_ROWS; ++r) acc = fma(ws.rho[r] * ws.A[r][i], ws.A[r][j], acc);
+        ws.K[i][j] = acc;
+        ws.K[j][i] = acc;
+      }
+      __syncwarp();
+      for (int j = 0; j < NV; ++j) {             // right-looking Cholesky, lane i owns row i
+        const double rs = rsqrt(ws.K[j][j]);
+        __syncwarp();
+        if (lane == j) { ws.K[j][j] = ws.K[j][j] * rs; ws.rdiag[j] = rs; }
+        if (lane > j && lane < NV) ws.K[lane][j] *= rs;
+        __syncwarp();
+        if (lane > j && lane < NV) {
+          const double lij = ws.K[lane][j];
+          for (int k2 = j + 1; k2 <= lane; ++k2) ws.K[lane][k2] = fma(-lij, ws.K[k2][j], ws.K[lane][k2]);
+        }
+        __syncwarp();
+      }
+      if (lane < NV) {                           // column `lane` of K^-1: L L' y = e_lane
+        double y[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) y[i] = (i == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          y[j] *= ws.rdiag[j];
+#pragma unroll
+          for (int i = j + 1; i < NV; ++i) y[i] = fma(-ws.K[i][j], y[j], y[i]);
+        }
+#pragma unroll
+        for (int j = NV - 1; j >= 0; --j) {
+          kinv[j] = y[j] * ws.rdiag[j];
+#pragma unroll
+          for (int i = 0; i < j; ++i) y[i] = fma(-ws.K[j][i], kinv[j], y[i]);
+        }
+      }
+      // ---- iterations ---------------------------------------------------------------------------------------------
+      SegStats s{0, 0, 0, 0, 0, 0};
+      for (int it = 0; it < pl.segment_iters; ++it) {
+        const bool check = (it == pl.segment_iters - 1);
+        double z[CW_K], w[CW_K], rhs[NV];
+#pragma unroll
+        for (int k = 0; k < CW_K; ++k) {
+          z[k] = clipd(v[k], lo[k], hi[k]);
+          w[k] = rho[k] * fma(2.0, z[k], -v[k]);
+        }
+        at_reduce(w, rhs);
+        double xi = 0.0;
+        if (lane < NV) {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) xi = fma(kinv[j], rhs[j] - st.q[j], xi);
+        }
+#pragma unroll
+        for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(FULL, xi, i);
+        double zt[CW_K];
+#pragma unroll
+        for (int k = 0; k < CW_K; ++k) {
+          double acc = 0.0;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) acc = fma(a[k][i], x[i], acc);
+          zt[k] = acc;
+        }
+        if (!check) {
+#pragma unroll
+          for (int k = 0; k < CW_K; ++k) v[k] = fma(pl.relax, zt[k] - z[k], v[k]);
+          continue;
+        }
+        double t1[CW_K], t2[CW_K];
+        double rp = 0.0, nd = 0.0, sup = 0.0, bad = 0.0;
+#pragma unroll
+        for (int k = 0; k < CW_K; ++k) {
+          const double vn = fma(pl.relax, zt[k] - z[k], v[k]);
+          const double zn = clipd(vn, lo[k], hi[k]);
+          rp = dmax(rp, fabs(zt[k] - zn));
+          t1[k] = rho[k] * (fma(2.0 - pl.relax, z[k], (pl.relax - 1.0) * zt[k]) - zn);
+          const double dy = rho[k] * ((vn - zn) - (v[k] - z[k]));
+          t2[k] = dy;
+          if (!FIRST_PASS) {
+            nd = dmax(nd, fabs(dy));
+            if (dy > 0.0) { if (hi[k] < BIG) sup = fma(hi[k], dy, sup); else bad = dmax(bad, dy); }
+            else if (dy < 0.0) { if (lo[k] > -BIG) sup = fma(lo[k], dy, sup); else bad = dmax(bad, -dy); }
+          }
+          const bool a_now = (vn < lo[k]) || (vn > hi[k]);
+          double vnew = vn;
+          if (a_now && (aprev[k] || !pl.hysteresis) && e[k] < pl.n_rung - 1) {
+            e[k] += 1;
+            vnew = fma(pl.lad_ratio[e[k]], vn - zn, zn);
+          } else if (!a_now && (!aprev[k] || !pl.hysteresis) && e[k] > 0) {
+            e[k] = pl.drop_all ? 0 : e[k] - 1;
+          }
+          aprev[k] = a_now;
+          v[k] = vnew;
+        }
+        double o1[NV];
+        at_reduce(t1, o1);
+        double rd = 0.0;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) rd = dmax(rd, fabs(o1[i]));
+        s.rp = warp_max(rp);
+        s.rd = rd;
+        if (!FIRST_PASS) {
+          double o2[NV];
+          at_reduce(t2, o2);
+          double atdy = 0.0;
+#pragma unroll
+          for (int i = 0; i < NV; ++i) atdy = dmax(atdy, fabs(o2[i]));
+          s.atdy = atdy;
+          s.nd = warp_max(nd);
+          s.bad = warp_max(bad);
+          s.sup = warp_sum(sup);
+        }
+      }
+      out.iters += pl.segment_iters;
+      if (s.rp <= eps_p && s.rd <= eps_d) conv = true;
+      else if (!FIRST_PASS && s.nd > 1e-9 && s.atdy <= P.eps_inf * s.nd && s.sup < -P.eps_inf * s.nd &&
+               s.bad <= P.eps_inf * s.nd) { conv = true; cert = true; }
+    }
+    double step = 0.0;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) step = dmax(step, fabs(x[i] - pb.U[i]));
+    __syncwarp();
+    if (lane < NV) { pb.U[lane] = x[lane]; pb.x[lane] = x[lane]; }
+    __syncwarp();
+    step_prev = step;
+    if (cert) { infeasible = true; done = true; }
+    else if (conv && step < P.step_tol) { done = true; out.status = 0; }
+    else if (!conv && FIRST_PASS) done = true;
+    else if (!conv && ++fails >= P.max_fail_rounds) done = true;
+  }
+  if (infeasible) out.status = 2;
+  __syncwarp();
+  if (lane < NV) pb.U[lane] = clipd(pb.U[lane], P.umin[lane & 1], P.umax[lane & 1]);
+  __syncwarp();
+  return out;
+}
+
+}  // namespace mpcb

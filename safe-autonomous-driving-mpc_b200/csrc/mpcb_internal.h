@@ -17,6 +17,7 @@ int cuda_fail(cudaError_t e, const char* where);
 
 struct mpcb_ctx {
   int device;
+  int n_sm = 148;
   mpcb_params params;
   mpcb::DevParams dp;
   mpcb::DevTable dt;

@@ -557,18 +557,14 @@ MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const 
 // ------------------------------------------------------------------------------------------------
 struct SolveOut { int status, rounds, iters; bool const_infeasible; };
 
-// FIRST_PASS = true : two-level policy only; a QP it cannot close ends the attempt (status MPCB_MAXITER = "not
-//                      certified"), no infeasibility verdict other than the rigorous screens.
-// FIRST_PASS = false: robust ladder with OSQP's infeasibility certificate; inexact Gauss-Newton: the QP of a round is
-//                      solved only as accurately as the previous SQP step warrants (P.qp_forcing).
-template <bool FIRST_PASS, class ST>
-MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const ST& st, bool live) {
-  SolveOut out{MPCB_MAXITER, 0, 0, false};
-  // Bounds of the rows that are exactly affine in U (speed, obstacle), and a rigorous screen: such a row that
-  // cannot be met anywhere inside the control box makes the problem infeasible whatever the other rows do
-  // (all coefficients are >= 0, so the row's extreme over the box sits at b = u2_min resp. u2_max).  Those rows
-  // are dropped from the QP (the solve then returns the best controls for the remaining rows) and the problem is
-  // flagged infeasible at once instead of waiting for an ADMM certificate.
+// Bounds of the rows that are exactly affine in U (speed, obstacle), and a rigorous screen: such a row that
+// cannot be met anywhere inside the control box makes the problem infeasible whatever the other rows do
+// (all coefficients are >= 0, so the row's extreme over the box sits at b = u2_min resp. u2_max).  Those rows
+// are dropped from the QP (the solve then returns the best controls for the remaining rows) and the problem is
+// flagged infeasible at once instead of waiting for an ADMM certificate.  Also: table hints, warm start
+// (trajectory_tracking.py:223-246) clipped to the bounds as scipy does (_slsqp_py.py:322).  Returns "screened".
+template <class ST>
+MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const ST& st) {
   bool screened = false;
 #pragma unroll
   for (int j = 0; j < NH; ++j) {
@@ -597,7 +593,17 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
   warm_start(T, P, pb.x0, pb.obs, pb.n_obs, pb.U);
 #pragma unroll
   for (int i = 0; i < NV; ++i) pb.U[i] = clipd(pb.U[i], P.umin[i & 1], P.umax[i & 1]);  // scipy clips x0 to the bounds
+  return screened;
+}
 
+// FIRST_PASS = true : two-level policy only; a QP it cannot close ends the attempt (status MPCB_MAXITER = "not
+//                      certified"), no infeasibility verdict other than the rigorous screens.
+// FIRST_PASS = false: robust ladder with OSQP's infeasibility certificate; inexact Gauss-Newton: the QP of a round is
+//                      solved only as accurately as the previous SQP step warrants (P.qp_forcing).
+template <bool FIRST_PASS, class ST>
+MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const ST& st, bool live) {
+  SolveOut out{MPCB_MAXITER, 0, 0, false};
+  const bool screened = prologue(T, P, pb, st);
   bool done = !live;
   bool infeasible = screened;
   out.const_infeasible = screened;
