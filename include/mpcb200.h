@@ -71,6 +71,7 @@ typedef struct mpcb_params {
   int fast_max_segments;           /* default 4 */
   int fast_segment_iters;          /* default 2 */
   int coop_pass2;                  /* robust pass executed by one warp per problem (latency), default 1 */
+  int coop_max_batch;              /* batches up to this size run the first pass one warp per problem too, default 2048 */
 } mpcb_params;
 
 typedef struct mpcb_ctx* mpcb_handle;

@@ -139,6 +139,7 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
 // Warp-per-problem kernel (mpcb_coop.cuh): the robust pass over the work list, and whole small batches.
 // ------------------------------------------------------------------------------------------------
 constexpr int COOP_WARPS = 4;
+constexpr size_t COOP_SMEM = sizeof(WarpShared) * COOP_WARPS;
 
 template <bool FIRST_PASS>
 __global__ void __launch_bounds__(COOP_WARPS * 32)
@@ -148,9 +149,9 @@ mpcb_coop_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
                  double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
                  int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
                  unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count) {
-  __shared__ WarpShared sh[COOP_WARPS];
+  extern __shared__ double coop_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  WarpShared& ws = sh[wid];
+  WarpShared& ws = reinterpret_cast<WarpShared*>(coop_smem)[wid];
   const int n_work = idx ? min(*n_idx, B) : B;
   const int n_warps = gridDim.x * COOP_WARPS;
   for (int t = blockIdx.x * COOP_WARPS + wid; t < n_work; t += n_warps) {
@@ -457,25 +458,35 @@ static int ensure_fb(mpcb_handle h, int B) {
 // timed: bracket the passes with the handle's events (single-stream callers only).
 static int launch_solve(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs, double* U_out,
                         double* Xpred_out, double* obj_out, int* status_out, int* iters_out, double* cmin_out,
-                        unsigned long long* active_out, cudaStream_t st, int* fb, bool timed) {
+                        unsigned long long* active_out, cudaStream_t st, int* fb, bool timed, bool whole_call = true) {
   const int grid = (B + SOLVE_THREADS - 1) / SOLVE_THREADS;
   CK(cudaFuncSetAttribute(mpcb_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
   CK(cudaFuncSetAttribute(mpcb_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
+  CK(cudaFuncSetAttribute(mpcb_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM));
+  CK(cudaFuncSetAttribute(mpcb_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM));
   if (timed) CK(cudaEventRecord(h->ev0, st));
   if (h->params.fast_pass) {
     int* fb_count = fb;
     int* fb_list = fb + 1;
     CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
-    mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
-                                                                    U_out, Xpred_out, obj_out, status_out, iters_out,
-                                                                    cmin_out, active_out, fb_list, fb_count);
+    if (whole_call && B <= h->params.coop_max_batch) {   // (parts of a larger call keep the shape of the whole call)
+      // small batch: too few problems to fill the GPU with one thread each -> one warp per problem, for latency
+      const int g1 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * 4);
+      mpcb_coop_kernel<true><<<g1, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs, U_out,
+                                                            Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
+                                                            fb_list, fb_count);
+    } else {
+      mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
+                                                                      U_out, Xpred_out, obj_out, status_out, iters_out,
+                                                                      cmin_out, active_out, fb_list, fb_count);
+    }
     CK(cudaGetLastError());
     if (timed) CK(cudaEventRecord(h->ev_mid, st));
     // second pass over whatever the first did not certify
     if (h->params.coop_pass2) {
       // one warp per problem: the leftovers are few and hard, what matters is their latency
       const int g2 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * 4);
-      mpcb_coop_kernel<false><<<g2, COOP_WARPS * 32, 0, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs, U_out,
+      mpcb_coop_kernel<false><<<g2, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs, U_out,
                                                              Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
                                                              nullptr, nullptr);
     } else {
@@ -596,7 +607,7 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
     rc = launch_solve(h, (int)n, (double*)(w + o_x0) + lo * 5, (double*)(w + o_obs) + lo * 4, (int*)(w + o_n) + lo,
                       dU + lo * 10, dX ? dX + lo * 30 : nullptr, dobj ? dobj + lo : nullptr, dst ? dst + lo : nullptr,
                       dit ? dit + lo * 2 : nullptr, dcm ? dcm + lo : nullptr, dac ? dac + lo : nullptr, st,
-                      h->fb + lo + c, false);
+                      h->fb + lo + c, false, false);
     if (rc != MPCB_OK) return rc;
     CK(cudaMemcpyAsync(U_out + lo * 10, dU + lo * 10, n * 80, cudaMemcpyDeviceToHost, st));
     if (Xpred_out) CK(cudaMemcpyAsync(Xpred_out + lo * 30, dX + lo * 30, n * 240, cudaMemcpyDeviceToHost, st));

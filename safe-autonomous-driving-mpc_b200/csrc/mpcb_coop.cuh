@@ -26,6 +26,8 @@ struct WarpShared {
   double rho[CW_ROWS];
   double K[NV][NV + 1];                 // K, then its Cholesky factor (lower)
   double rdiag[NV];
+  double red[32][2 * NV + 1];           // per-lane partial sums of the A't reductions (odd stride: conflict free)
+  double vec[2][NV];                    // reduced vector / iterate, broadcast to the lanes
   double scal[4];                       // lane-0 scalars broadcast through shared memory
   int iflag[2];
 };
@@ -108,15 +110,31 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
 #pragma unroll
   for (int k = 0; k < CW_K; ++k) { v[k] = 0.0; rho[k] = 0.0; e[k] = 0; aprev[k] = false; }
 
-  // all-reduced  out[i] = sum_rows a_r[i] t_r
-  auto at_reduce = [&](const double (&t)[CW_K], double (&o)[NV]) {
+  // o[i] = sum over all rows of a_r[i] t_r for NVEC right-hand sides at once, result on lanes 0..9 (lane i gets
+  // component i).  Partial sums go through shared memory: every lane writes its 10 partials, lanes (i, g) with
+  // i = lane % 10, g = lane / 10 < 3 add up a third of the lanes each, two shuffles combine the thirds.
+  auto at_reduce = [&](const double (&t0)[CW_K], const double (&t1)[CW_K], bool two, double& o0, double& o1) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-      double p = 0.0;
+      double p = 0.0, q2 = 0.0;
 #pragma unroll
-      for (int k = 0; k < CW_K; ++k) p = fma(a[k][i], t[k], p);
-      o[i] = warp_sum(p);
+      for (int k = 0; k < CW_K; ++k) { p = fma(a[k][i], t0[k], p); q2 = fma(a[k][i], t1[k], q2); }
+      ws.red[lane][i] = p;
+      if (two) ws.red[lane][NV + i] = q2;
     }
+    __syncwarp();
+    const int i = lane % NV, g = lane / NV;
+    const int l0 = g * 11, l1 = (g == 2) ? 32 : l0 + 11;
+    double s0 = 0.0, s1 = 0.0;
+    if (g < 3) {
+      for (int l = l0; l < l1; ++l) {
+        s0 += ws.red[l][i];
+        if (two) s1 += ws.red[l][NV + i];
+      }
+    }
+    o0 = s0 + __shfl_down_sync(FULL, s0, 10) + __shfl_down_sync(FULL, s0, 20);
+    o1 = two ? s1 + __shfl_down_sync(FULL, s1, 10) + __shfl_down_sync(FULL, s1, 20) : 0.0;
+    __syncwarp();
   };
 
   for (int round = 0; round < max_rounds && !done; ++round) {
@@ -206,20 +224,25 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
       SegStats s{0, 0, 0, 0, 0, 0};
       for (int it = 0; it < pl.segment_iters; ++it) {
         const bool check = (it == pl.segment_iters - 1);
-        double z[CW_K], w[CW_K], rhs[NV];
+        double z[CW_K], w[CW_K];
 #pragma unroll
         for (int k = 0; k < CW_K; ++k) {
           z[k] = clipd(v[k], lo[k], hi[k]);
           w[k] = rho[k] * fma(2.0, z[k], -v[k]);
         }
-        at_reduce(w, rhs);
-        double xi = 0.0;
+        double r0, r1;
+        at_reduce(w, w, false, r0, r1);
+        if (lane < NV) ws.vec[0][lane] = r0 - st.q[lane];
+        __syncwarp();
         if (lane < NV) {
+          double xi = 0.0;
 #pragma unroll
-          for (int j = 0; j < NV; ++j) xi = fma(kinv[j], rhs[j] - st.q[j], xi);
+          for (int j = 0; j < NV; ++j) xi = fma(kinv[j], ws.vec[0][j], xi);
+          ws.vec[1][lane] = xi;
         }
+        __syncwarp();
 #pragma unroll
-        for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(FULL, xi, i);
+        for (int i = 0; i < NV; ++i) x[i] = ws.vec[1][i];
         double zt[CW_K];
 #pragma unroll
         for (int k = 0; k < CW_K; ++k) {
@@ -259,20 +282,12 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
           aprev[k] = a_now;
           v[k] = vnew;
         }
-        double o1[NV];
-        at_reduce(t1, o1);
-        double rd = 0.0;
-#pragma unroll
-        for (int i = 0; i < NV; ++i) rd = dmax(rd, fabs(o1[i]));
+        double o1, o2;
+        at_reduce(t1, t2, !FIRST_PASS, o1, o2);
         s.rp = warp_max(rp);
-        s.rd = rd;
+        s.rd = warp_max(lane < NV ? fabs(o1) : 0.0);
         if (!FIRST_PASS) {
-          double o2[NV];
-          at_reduce(t2, o2);
-          double atdy = 0.0;
-#pragma unroll
-          for (int i = 0; i < NV; ++i) atdy = dmax(atdy, fabs(o2[i]));
-          s.atdy = atdy;
+          s.atdy = warp_max(lane < NV ? fabs(o2) : 0.0);
           s.nd = warp_max(nd);
           s.bad = warp_max(bad);
           s.sup = warp_sum(sup);
