@@ -49,7 +49,7 @@ __device__ __forceinline__ void finalize(const DevTable& T, const DevParams& P, 
   // final evaluation at U*: predict, cost, constraint rows in the reference's order
   double X[NH + 1][5];
   double cost;
-  rollout_values(T, P, pb.x0, pb.U, X, cost);
+  rollout_values(T, P, pb.x0, pb.U, X, cost, pb.hint);
   double cmin = BIG;
   unsigned long long act = 0ull;
   int row = 0;

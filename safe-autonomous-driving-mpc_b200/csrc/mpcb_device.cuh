@@ -119,21 +119,26 @@ MPCB_HD void lookup_state(const DevTable& T, double s, double (&val)[4], double 
 // Same as lookup_state, with the table segment remembered between calls: consecutive predicted positions (and the
 // same step in the next linearisation round) land in the same or a neighbouring segment, so a short walk from the
 // previous index replaces the binary search.  `hint` is updated.
+MPCB_HD int seg_index_hint(const double* __restrict__ sa, int K, double x, int& hint) {
+  int i = hint < 1 ? 1 : (hint > K - 1 ? K - 1 : hint);
+  bool found = false;
+  for (int t = 0; t < 6 && !found; ++t) {
+    if (i < K - 1 && MPCB_LDG(sa + i) < x) ++i;
+    else if (i > 1 && MPCB_LDG(sa + i - 1) >= x) --i;
+    else found = true;
+  }
+  if (!found) i = seg_index(sa, K, x);
+  hint = i;
+  return i;
+}
+
 MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], double (&slope)[4], int& hint) {
   if (s >= T.s_max) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) { val[c] = T.last[c]; slope[c] = 0.0; }
     return;
   }
-  int i = hint < 1 ? 1 : (hint > T.K - 1 ? T.K - 1 : hint);
-  bool found = false;
-  for (int t = 0; t < 6 && !found; ++t) {
-    if (i < T.K - 1 && MPCB_LDG(T.s + i) < s) ++i;
-    else if (i > 1 && MPCB_LDG(T.s + i - 1) >= s) --i;
-    else found = true;
-  }
-  if (!found) i = seg_index(T.s, T.K, s);
-  hint = i;
+  const int i = seg_index_hint(T.s, T.K, s, hint);
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double inv = 1.0 / (x_hi - x_lo);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
@@ -155,9 +160,9 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
   }
 }
 
-MPCB_HD void lookup_control(const DevTable& T, double s, double (&u)[2]) {
+MPCB_HD void lookup_control(const DevTable& T, double s, double (&u)[2], int& hint) {
   if (s >= T.s_max) { u[0] = 0.0; u[1] = 0.0; return; }
-  const int i = seg_index(T.s, T.Ku, s);
+  const int i = (hint > 0) ? seg_index_hint(T.s, T.Ku, s, hint) : (hint = seg_index(T.s, T.Ku, s));
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
   const double ul0 = MPCB_LDG(T.u + 2 * (i - 1)), ul1 = MPCB_LDG(T.u + 2 * (i - 1) + 1);
@@ -167,8 +172,11 @@ MPCB_HD void lookup_control(const DevTable& T, double s, double (&u)[2]) {
 }
 
 // warm start, trajectory_tracking.py:223-246 (unclipped)
+// hints[j] (optional) receives the table segment of the j-th probe position s0 + j h v0, a good first guess for the
+// lookups of the rollout.
 MPCB_HD void warm_start(const DevTable& T, const DevParams& P, const double (&x0)[5],
-                                           const double (&obs)[2][2], int n_obs, double (&U)[NV]) {
+                                           const double (&obs)[2][2], int n_obs, double (&U)[NV], int* hints = nullptr) {
+  int hint = 0;          // 0: first probe uses the binary search, the following ones walk from it
   double s_cur = x0[0];
   const double v_cur = x0[4];
   bool brake = false;
@@ -178,7 +186,8 @@ MPCB_HD void warm_start(const DevTable& T, const DevParams& P, const double (&x0
     for (int k = 0; k < 2; ++k)
       if (k < n_obs && (obs[k][0] - s_cur) < P.brake_lookahead) brake = true;
     double ur[2];
-    lookup_control(T, s_cur, ur);
+    lookup_control(T, s_cur, ur, hint);
+    if (hints) hints[j] = hint;
     U[2 * j] = ur[0];
     U[2 * j + 1] = brake ? P.brake_guess : ur[1];
     s_cur += v_cur * P.h;
@@ -189,7 +198,11 @@ MPCB_HD void warm_start(const DevTable& T, const DevParams& P, const double (&x0
 // Values-only rollout: X[6][5], cost, and constraint rows in the reference's order.
 // ------------------------------------------------------------------------------------------------
 MPCB_HD void rollout_values(const DevTable& T, const DevParams& P, const double (&x0)[5],
-                                               const double (&U)[NV], double (&X)[NH + 1][5], double& cost) {
+                                               const double (&U)[NV], double (&X)[NH + 1][5], double& cost,
+                                               const int* hints = nullptr) {
+  int hloc[NH + 1];
+#pragma unroll
+  for (int j = 0; j <= NH; ++j) hloc[j] = hints ? hints[j] : 1;
 #pragma unroll
   for (int c = 0; c < 5; ++c) X[0][c] = x0[c];
   double val[4], slope[4];
@@ -197,7 +210,7 @@ MPCB_HD void rollout_values(const DevTable& T, const DevParams& P, const double 
 #pragma unroll
   for (int j = 0; j < NH; ++j) {
     const double s = X[j][0], d = X[j][1], o = X[j][2], k = X[j][3], v = X[j][4];
-    lookup_state(T, s, val, slope);
+    lookup_state_hint(T, s, val, slope, hloc[j]);
     if (j > 0) {  // tracking terms of step j use the lookup at s_j
       const double rd = d - val[0], ro = o - val[1], rv = v - val[3];
       c_acc += P.wd * (rd * rd);
@@ -211,7 +224,7 @@ MPCB_HD void rollout_values(const DevTable& T, const DevParams& P, const double 
     X[j + 1][4] = v + P.h * U[2 * j + 1];
   }
   {
-    lookup_state(T, X[NH][0], val, slope);
+    lookup_state_hint(T, X[NH][0], val, slope, hloc[NH]);
     const double rd = X[NH][1] - val[0], ro = X[NH][2] - val[1], rv = X[NH][4] - val[3];
     c_acc += P.wd * (rd * rd);
     c_acc += P.wo * (ro * ro);

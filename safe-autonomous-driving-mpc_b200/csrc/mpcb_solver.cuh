@@ -588,9 +588,8 @@ MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const 
       st.hio[N_OBSROW * k + 4 + (j - 1)] = (!on || dead2) ? BIG : h2;
       screened |= dead1 | dead2;
     }
-#pragma unroll
-  for (int j = 0; j <= NH; ++j) pb.hint[j] = 1;
-  warm_start(T, P, pb.x0, pb.obs, pb.n_obs, pb.U);
+  warm_start(T, P, pb.x0, pb.obs, pb.n_obs, pb.U, pb.hint);
+  pb.hint[NH] = pb.hint[NH - 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) pb.U[i] = clipd(pb.U[i], P.umin[i & 1], P.umax[i & 1]);  // scipy clips x0 to the bounds
   return screened;
