@@ -194,6 +194,38 @@ int mpcb_hs_nodes(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int
                   const double* vmin_nodes, const double* vmax_nodes, double* node_rows, double* ctrl_rows,
                   double* cost_terms, double* cost, double* cost_grad, void* cuda_stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Batched closed loop on the device (the callers either side of the solve path): ObstaclesFSM.update
+ * (trajectory_tracking.py:330-374) -> solve -> explicit-Euler plant step (:404-406), repeated while
+ * s <= s_max - 1 (:395), for B vehicles at once without leaving the GPU.
+ * --------------------------------------------------------------------------------------------------------- */
+typedef struct mpcb_scenario {      /* mirrors ObstaclesFSM.__init__, trajectory_tracking.py:285-308 */
+  int dynamic_obstacle, traffic_light;
+  double obs_trigger_s, obs_start_s, obs_v, obs_end_s;     /* :294-299 */
+  double tl_pos, tl_trigger_s, tl_stop_duration;           /* :302-308 */
+} mpcb_scenario;
+
+typedef struct mpcb_sim* mpcb_sim_handle;
+
+/* which = 2: constants as committed (:294-308); which = 3: the commented trajectory3 block (:313-327) */
+int mpcb_scenario_default(mpcb_scenario* s, int which);
+/* B vehicles on the solver context h.  scen: HOST array of n_scen = 1 (shared) or B scenarios.  x_init: HOST [B][5]
+ * or NULL for the reference's start [0,0,0,0,0.5] (:382).  history_steps > 0 records that many steps on the device. */
+int mpcb_sim_create(mpcb_sim_handle* out, mpcb_handle h, int B, const mpcb_scenario* scen, int n_scen,
+                    const double* x_init, int history_steps);
+int mpcb_sim_destroy(mpcb_sim_handle s);
+/* n_steps closed-loop steps, asynchronous on cuda_stream (3 + the solver's launches per step, no host round trip).
+ * Vehicles that have passed s_max - 1 are frozen. */
+int mpcb_sim_step(mpcb_sim_handle s, int n_steps, void* cuda_stream);
+/* number of vehicles still driving (synchronises the stream) */
+int mpcb_sim_alive(mpcb_sim_handle s, int* n_alive, void* cuda_stream);
+/* HOST outputs (any may be NULL): current states [B][5], steps driven [B], steps whose solve was not MPCB_SOLVED [B] */
+int mpcb_sim_state(mpcb_sim_handle s, double* x, int* steps, int* n_unsolved, void* cuda_stream);
+/* recorded history, HOST outputs sized [n_recorded][B]...: state before each step [.][5], applied control [.][2],
+ * position of the moving car (NaN when absent), solver status (-1 once frozen), light colour (0 red, 1 green) */
+int mpcb_sim_history(mpcb_sim_handle s, int* n_recorded, double* hist_x, double* hist_u, double* hist_obs,
+                     int* hist_status, int* hist_tl, void* cuda_stream);
+
 const char* mpcb_strerror(int code);
 const char* mpcb_last_cuda_error(void);
 int mpcb_abi_version(void);

@@ -7,8 +7,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.environ.get("MPCB_LIB") or os.path.join(HERE, "libmpcb200.so")   # MPCB_LIB: development variants
-SOURCES = ["mpcb_api.cu", "mpcb_planner.cu"]
-HEADERS = ["mpcb_device.cuh", "mpcb_solver.cuh", "mpcb_planner.cuh", "mpcb_internal.h"]
+SOURCES = ["mpcb_api.cu", "mpcb_planner.cu", "mpcb_sim.cu"]
+HEADERS = ["mpcb_device.cuh", "mpcb_solver.cuh", "mpcb_planner.cuh", "mpcb_internal.h", "mpcb_coop.cuh", "mpcb_params.h"]
 
 
 def nvcc_path():

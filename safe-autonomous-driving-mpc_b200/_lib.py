@@ -51,6 +51,15 @@ class PlannerParams(C.Structure):
     ]
 
 
+class Scenario(C.Structure):
+    """struct mpcb_scenario (include/mpcb200.h); mirrors ObstaclesFSM.__init__, trajectory_tracking.py:285-308."""
+    _fields_ = [
+        ("dynamic_obstacle", C.c_int), ("traffic_light", C.c_int),
+        ("obs_trigger_s", C.c_double), ("obs_start_s", C.c_double), ("obs_v", C.c_double), ("obs_end_s", C.c_double),
+        ("tl_pos", C.c_double), ("tl_trigger_s", C.c_double), ("tl_stop_duration", C.c_double),
+    ]
+
+
 # every symbol include/mpcb200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "mpcb_default_params": (C.c_int, [C.POINTER(Params)]),
@@ -78,6 +87,13 @@ SYMBOLS = {
     "mpcb_planner_default_params": (C.c_int, [C.POINTER(PlannerParams)]),
     "mpcb_hs_eval": (C.c_int, [C.c_void_p, C.POINTER(PlannerParams), C.c_int, C.c_int] + [C.c_void_p] * 5 + [C.c_void_p]),
     "mpcb_hs_nodes": (C.c_int, [C.c_void_p, C.POINTER(PlannerParams), C.c_int, C.c_int] + [C.c_void_p] * 9 + [C.c_void_p]),
+    "mpcb_scenario_default": (C.c_int, [C.POINTER(Scenario), C.c_int]),
+    "mpcb_sim_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.POINTER(Scenario), C.c_int, C.c_void_p, C.c_int]),
+    "mpcb_sim_destroy": (C.c_int, [C.c_void_p]),
+    "mpcb_sim_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mpcb_sim_alive": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
+    "mpcb_sim_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpcb_sim_history": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)] + [C.c_void_p] * 5 + [C.c_void_p]),
     "mpcb_strerror": (C.c_char_p, [C.c_int]),
     "mpcb_last_cuda_error": (C.c_char_p, []),
     "mpcb_abi_version": (C.c_int, []),

@@ -53,7 +53,8 @@ __device__ __forceinline__ void coop_row(const DevParams& P, const Store<1, 0>& 
   if (r < ROW_LANE) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) if (i == r) a[i] = 1.0;
-    lo = P.umin[r & 1]; hi = P.umax[r & 1]; inrm = 1.0; exists = true;
+    if (r & 1) { lo = st.blo[r >> 1]; hi = st.bhi[r >> 1]; } else { lo = P.umin[0]; hi = P.umax[0]; }
+    inrm = 1.0; exists = true;
   } else if (r < ROW_V) {
     const int q = r - ROW_LANE, jj = q >> 1;
     const double al = (q & 1) ? P.alpha_lane[2] : 0.0;
@@ -310,7 +311,9 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
     else if (!conv && FIRST_PASS) done = true;
     else if (!conv && ++fails >= P.max_fail_rounds) done = true;
   }
-  if (infeasible) out.status = 2;
+  // an infeasibility verdict is final only on a point the pass actually converged to (or, in the robust pass, gave
+  // up on): a first pass that could not close its QP hands the problem over whatever the screens said
+  if (infeasible && (!FIRST_PASS || out.status == 0)) out.status = 2;
   __syncwarp();
   if (lane < NV) pb.U[lane] = clipd(pb.U[lane], P.umin[lane & 1], P.umax[lane & 1]);
   __syncwarp();

@@ -1,0 +1,274 @@
+// mpcb_sim.cu -- batched closed loop on the device: the callers either side of the solve path.
+//
+//   obstacle-set producer   ObstaclesFSM.update            trajectory_tracking.py:330-374
+//   plant step              x += dt * dynamics(x, u0, k_ref(s))   trajectory_tracking.py:404-406 (dynamics :50-67)
+//   loop condition          while current_s <= s_max - 1.0         trajectory_tracking.py:395
+//
+// One simulation object holds B vehicles (each with its own scenario constants and FSM state).  A step is three
+// launches on one stream -- FSM kernel -> mpcb_solve_batch -> plant kernel -- with no host round trip, so a
+// Monte-Carlo of whole drives never leaves the GPU; histories are recorded into device buffers when asked for.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "mpcb200.h"
+#include "mpcb_internal.h"
+
+namespace mpcb {
+
+struct DevScenario {          // per vehicle, mirrors ObstaclesFSM.__init__ (:285-308)
+  double obs_trigger_s, obs_start_s, obs_v, obs_end_s;
+  double tl_pos, tl_trigger_s, tl_stop_duration;
+  int dynamic_obstacle, traffic_light;
+};
+
+enum { F_OBS_ACTIVE = 1, F_OBS_TRIGGERED = 2, F_TL_GREEN = 4, F_TL_WAITING = 8 };
+
+// ObstaclesFSM.update for every vehicle that is still driving (:330-374); car first, then light (:349, :362)
+__global__ void __launch_bounds__(128)
+mpcb_fsm_kernel(int B, double dt, double s_stop, const double* __restrict__ x, const DevScenario* __restrict__ scen,
+                double* __restrict__ fsm_f, int* __restrict__ fsm_i, int* __restrict__ alive,
+                double* __restrict__ obs_sv, int* __restrict__ n_obs, int rec_t, double* __restrict__ hist_obs,
+                int* __restrict__ hist_tl) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double s = x[(size_t)b * 5], v = x[(size_t)b * 5 + 4];
+  const int live = (s <= s_stop) ? 1 : 0;                    // loop condition (:395), evaluated before the step
+  alive[b] = live;
+  int n = 0;
+  double o[4] = {0.0, 0.0, 0.0, 0.0};
+  double car_s = nan("");
+  int f = fsm_i[b];
+  if (live) {
+    const DevScenario sc = scen[b];
+    double obs_s = fsm_f[2 * b], timer = fsm_f[2 * b + 1];
+    if (sc.dynamic_obstacle) {
+      if (s >= sc.obs_trigger_s && !(f & F_OBS_TRIGGERED)) f |= F_OBS_TRIGGERED | F_OBS_ACTIVE;
+      if (f & F_OBS_ACTIVE) {
+        obs_s += sc.obs_v * dt;
+        if (obs_s > sc.obs_end_s) f &= ~F_OBS_ACTIVE;
+        else { o[0] = obs_s; o[1] = sc.obs_v; n = 1; car_s = obs_s; }
+      }
+    }
+    if (sc.traffic_light && !(f & F_TL_GREEN)) {
+      const double gap = sc.tl_pos - s;
+      if (0.0 < gap && gap < sc.tl_trigger_s) {
+        o[2 * n] = sc.tl_pos; o[2 * n + 1] = 0.0; ++n;
+        if (v < 0.1 && gap < 10.0) f |= F_TL_WAITING;
+      }
+      if (f & F_TL_WAITING) {
+        timer += dt;
+        if (timer >= sc.tl_stop_duration) { f |= F_TL_GREEN; f &= ~F_TL_WAITING; }
+      }
+    }
+    fsm_f[2 * b] = obs_s;
+    fsm_f[2 * b + 1] = timer;
+    fsm_i[b] = f;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) obs_sv[(size_t)b * 4 + k] = o[k];
+  n_obs[b] = n;
+  if (hist_obs && rec_t >= 0) {
+    hist_obs[(size_t)rec_t * B + b] = car_s;                 // position of the moving car, NaN when absent
+    hist_tl[(size_t)rec_t * B + b] = live ? ((f & F_TL_GREEN) ? 1 : 0) : -1;   // light colour returned by update()
+  }
+}
+
+// plant step (:404-406) for the vehicles that were alive at the start of the step
+__global__ void __launch_bounds__(128)
+mpcb_plant_kernel(const __grid_constant__ DevTable T, int B, double dt, double* __restrict__ x,
+                  const double* __restrict__ U, const int* __restrict__ status, const int* __restrict__ alive,
+                  int* __restrict__ steps, int* __restrict__ n_unsolved, int rec_t, double* __restrict__ hist_x,
+                  double* __restrict__ hist_u, int* __restrict__ hist_status) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int live = alive[b];
+  double xs[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) xs[c] = x[(size_t)b * 5 + c];
+  const double u1 = U[(size_t)b * NV], u2 = U[(size_t)b * NV + 1];
+  if (hist_x && rec_t >= 0) {                                // state and control of THIS step (before the update)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) hist_x[((size_t)rec_t * B + b) * 5 + c] = live ? xs[c] : nan("");
+    hist_u[((size_t)rec_t * B + b) * 2] = live ? u1 : nan("");
+    hist_u[((size_t)rec_t * B + b) * 2 + 1] = live ? u2 : nan("");
+    hist_status[(size_t)rec_t * B + b] = live ? status[b] : -1;
+  }
+  if (!live) return;
+  double val[4], slope[4];
+  lookup_state(T, xs[0], val, slope);                        // k_ref = get_state(current_s)[3]  (:404)
+  const double kref = val[2];
+  const double s = xs[0], o = xs[2], k = xs[3], v = xs[4];
+  // x + dt * [v, v o, v (k - k_ref), u1, u2]   (:50-67, :406); no FMA contraction: same rounding as numpy
+  x[(size_t)b * 5 + 0] = __dadd_rn(s, __dmul_rn(dt, v));
+  x[(size_t)b * 5 + 1] = __dadd_rn(xs[1], __dmul_rn(dt, __dmul_rn(v, o)));
+  x[(size_t)b * 5 + 2] = __dadd_rn(o, __dmul_rn(dt, __dmul_rn(v, __dadd_rn(k, -kref))));
+  x[(size_t)b * 5 + 3] = __dadd_rn(k, __dmul_rn(dt, u1));
+  x[(size_t)b * 5 + 4] = __dadd_rn(v, __dmul_rn(dt, u2));
+  steps[b] += 1;
+  if (status[b] != MPCB_SOLVED) n_unsolved[b] += 1;
+}
+
+__global__ void mpcb_count_alive_kernel(int B, double s_stop, const double* __restrict__ x, int* __restrict__ count) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int live = (b < B && x[(size_t)b * 5] <= s_stop) ? 1 : 0;
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
+
+}  // namespace mpcb
+
+using namespace mpcb;
+
+struct mpcb_sim {
+  mpcb_handle h;
+  int B, cap, t;              // vehicles, history capacity (steps), steps recorded so far
+  double dt, s_stop;
+  DevScenario* scen = nullptr;
+  double *x = nullptr, *fsm_f = nullptr, *obs_sv = nullptr, *U = nullptr;
+  int *fsm_i = nullptr, *alive = nullptr, *n_obs = nullptr, *status = nullptr, *steps = nullptr, *n_unsolved = nullptr,
+      *count = nullptr;
+  double *hist_x = nullptr, *hist_u = nullptr, *hist_obs = nullptr;
+  int *hist_status = nullptr, *hist_tl = nullptr;
+};
+
+extern "C" {
+
+int mpcb_scenario_default(mpcb_scenario* s, int which) {
+  if (!s) return MPCB_ERR_INVALID;
+  memset(s, 0, sizeof(*s));
+  if (which == 3) {            // trajectory3 constants, the commented block trajectory_tracking.py:313-327
+    s->obs_trigger_s = 5.0; s->obs_start_s = 150.0; s->obs_v = 4.0; s->obs_end_s = 850.0;
+    s->tl_pos = 2000.0; s->tl_trigger_s = 100.0; s->tl_stop_duration = 20.0;
+  } else {                     // trajectory2 constants as committed, :294-308
+    s->obs_trigger_s = 710.0; s->obs_start_s = 780.0; s->obs_v = 4.0; s->obs_end_s = 1050.0;
+    s->tl_pos = 550.0; s->tl_trigger_s = 100.0; s->tl_stop_duration = 20.0;
+  }
+  s->dynamic_obstacle = 1; s->traffic_light = 1;
+  return MPCB_OK;
+}
+
+int mpcb_sim_destroy(mpcb_sim_handle s) {
+  if (!s) return MPCB_ERR_INVALID;
+  cudaSetDevice(s->h->device);
+  void* ptrs[] = {s->scen, s->x, s->fsm_f, s->obs_sv, s->U, s->fsm_i, s->alive, s->n_obs, s->status, s->steps,
+                  s->n_unsolved, s->count, s->hist_x, s->hist_u, s->hist_obs, s->hist_status, s->hist_tl};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  delete s;
+  return MPCB_OK;
+}
+
+int mpcb_sim_create(mpcb_sim_handle* out, mpcb_handle h, int B, const mpcb_scenario* scen, int n_scen,
+                    const double* x_init, int history_steps) {
+  if (!out || !h || B < 1 || !scen || (n_scen != 1 && n_scen != B) || history_steps < 0) return MPCB_ERR_INVALID;
+  *out = nullptr;
+  CK(cudaSetDevice(h->device));
+  mpcb_sim* s = new (std::nothrow) mpcb_sim();
+  if (!s) return MPCB_ERR_NOMEM;
+  s->h = h; s->B = B; s->cap = history_steps; s->t = 0;
+  s->dt = h->params.dt;
+  s->s_stop = h->dt.s_max - 1.0;                                        // :395
+  auto fail = [&](int code) { mpcb_sim_destroy(s); return code; };
+  const size_t nb = (size_t)B;
+#define SIM_ALLOC(ptr, bytes) if (cudaMalloc((void**)&(ptr), (bytes)) != cudaSuccess) { cudaGetLastError(); return fail(MPCB_ERR_NOMEM); }
+  SIM_ALLOC(s->scen, nb * sizeof(DevScenario));
+  SIM_ALLOC(s->x, nb * 40); SIM_ALLOC(s->fsm_f, nb * 16); SIM_ALLOC(s->obs_sv, nb * 32); SIM_ALLOC(s->U, nb * 80);
+  SIM_ALLOC(s->fsm_i, nb * 4); SIM_ALLOC(s->alive, nb * 4); SIM_ALLOC(s->n_obs, nb * 4); SIM_ALLOC(s->status, nb * 4);
+  SIM_ALLOC(s->steps, nb * 4); SIM_ALLOC(s->n_unsolved, nb * 4); SIM_ALLOC(s->count, 4);
+  if (history_steps > 0) {
+    const size_t nt = (size_t)history_steps * nb;
+    SIM_ALLOC(s->hist_x, nt * 40); SIM_ALLOC(s->hist_u, nt * 16); SIM_ALLOC(s->hist_obs, nt * 8);
+    SIM_ALLOC(s->hist_status, nt * 4); SIM_ALLOC(s->hist_tl, nt * 4);
+  }
+#undef SIM_ALLOC
+  std::vector<DevScenario> hs(nb);
+  std::vector<double> hx(nb * 5), hf(nb * 2);
+  for (size_t b = 0; b < nb; ++b) {
+    const mpcb_scenario& c = scen[n_scen == 1 ? 0 : b];
+    hs[b] = DevScenario{c.obs_trigger_s, c.obs_start_s, c.obs_v, c.obs_end_s, c.tl_pos, c.tl_trigger_s,
+                        c.tl_stop_duration, c.dynamic_obstacle, c.traffic_light};
+    if (x_init) for (int k = 0; k < 5; ++k) hx[b * 5 + k] = x_init[b * 5 + k];
+    else { hx[b * 5] = hx[b * 5 + 1] = hx[b * 5 + 2] = hx[b * 5 + 3] = 0.0; hx[b * 5 + 4] = 0.5; }   // :382
+    hf[b * 2] = c.obs_start_s;                                          // obs_s = obs_start_s (:297)
+    hf[b * 2 + 1] = 0.0;
+  }
+  cudaError_t e;
+  if ((e = cudaMemcpy(s->scen, hs.data(), nb * sizeof(DevScenario), cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
+  if ((e = cudaMemcpy(s->x, hx.data(), nb * 40, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
+  if ((e = cudaMemcpy(s->fsm_f, hf.data(), nb * 16, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
+  if ((e = cudaMemset(s->fsm_i, 0, nb * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
+  if ((e = cudaMemset(s->steps, 0, nb * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
+  if ((e = cudaMemset(s->n_unsolved, 0, nb * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
+  *out = s;
+  return MPCB_OK;
+}
+
+int mpcb_sim_step(mpcb_sim_handle s, int n_steps, void* cuda_stream) {
+  if (!s || n_steps < 0) return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(s->h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int grid = (s->B + 127) / 128;
+  for (int k = 0; k < n_steps; ++k) {
+    const int rec = (s->t < s->cap) ? s->t : -1;
+    mpcb_fsm_kernel<<<grid, 128, 0, st>>>(s->B, s->dt, s->s_stop, s->x, s->scen, s->fsm_f, s->fsm_i, s->alive, s->obs_sv,
+                                          s->n_obs, rec, s->hist_obs, s->hist_tl);
+    CK(cudaGetLastError());
+    int rc = mpcb_solve_batch(s->h, s->B, s->x, s->obs_sv, s->n_obs, s->U, nullptr, nullptr, s->status, nullptr, nullptr,
+                              nullptr, st);
+    if (rc != MPCB_OK) return rc;
+    mpcb_plant_kernel<<<grid, 128, 0, st>>>(s->h->dt, s->B, s->dt, s->x, s->U, s->status, s->alive, s->steps,
+                                            s->n_unsolved, rec, s->hist_x, s->hist_u, s->hist_status);
+    CK(cudaGetLastError());
+    s->h->launches += 2;
+    s->t += 1;
+  }
+  return MPCB_OK;
+}
+
+int mpcb_sim_alive(mpcb_sim_handle s, int* n_alive, void* cuda_stream) {
+  if (!s || !n_alive) return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(s->h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  CK(cudaMemsetAsync(s->count, 0, 4, st));
+  mpcb_count_alive_kernel<<<(s->B + 127) / 128, 128, 0, st>>>(s->B, s->s_stop, s->x, s->count);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(n_alive, s->count, 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPCB_OK;
+}
+
+int mpcb_sim_state(mpcb_sim_handle s, double* x, int* steps, int* n_unsolved, void* cuda_stream) {
+  if (!s) return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(s->h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t nb = (size_t)s->B;
+  if (x) CK(cudaMemcpyAsync(x, s->x, nb * 40, cudaMemcpyDeviceToHost, st));
+  if (steps) CK(cudaMemcpyAsync(steps, s->steps, nb * 4, cudaMemcpyDeviceToHost, st));
+  if (n_unsolved) CK(cudaMemcpyAsync(n_unsolved, s->n_unsolved, nb * 4, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  return MPCB_OK;
+}
+
+int mpcb_sim_history(mpcb_sim_handle s, int* n_recorded, double* hist_x, double* hist_u, double* hist_obs,
+                     int* hist_status, int* hist_tl, void* cuda_stream) {
+  if (!s) return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(s->h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const int nt = s->t < s->cap ? s->t : s->cap;
+  if (n_recorded) *n_recorded = nt;
+  const size_t n = (size_t)nt * s->B;
+  if (n > 0) {
+    if (hist_x) CK(cudaMemcpyAsync(hist_x, s->hist_x, n * 40, cudaMemcpyDeviceToHost, st));
+    if (hist_u) CK(cudaMemcpyAsync(hist_u, s->hist_u, n * 16, cudaMemcpyDeviceToHost, st));
+    if (hist_obs) CK(cudaMemcpyAsync(hist_obs, s->hist_obs, n * 8, cudaMemcpyDeviceToHost, st));
+    if (hist_status) CK(cudaMemcpyAsync(hist_status, s->hist_status, n * 4, cudaMemcpyDeviceToHost, st));
+    if (hist_tl) CK(cudaMemcpyAsync(hist_tl, s->hist_tl, n * 4, cudaMemcpyDeviceToHost, st));
+  }
+  CK(cudaStreamSynchronize(st));
+  return MPCB_OK;
+}
+
+}  // extern "C"

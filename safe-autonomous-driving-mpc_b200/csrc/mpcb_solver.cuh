@@ -79,7 +79,7 @@ struct Store {
   typedef typename ColSel<(LEVEL >= 3), S>::type C3;
   static constexpr int N1 = 2 * M_ROWS + 2 * N_OBSROW + 2 * N_DO;     // 140
   static constexpr int N2 = NTRI + NV + NV + N_LANE;                  // 83
-  static constexpr int N3 = NTRI + N_LANE + NH;                       // 68
+  static constexpr int N3 = NTRI + N_LANE + NH + 2 * NH;              // 78
   static constexpr int SHARED = (LEVEL >= 1 ? N1 : 0) + (LEVEL >= 2 ? N2 : 0) + (LEVEL >= 3 ? N3 : 0);
   static constexpr int LOCAL = N1 + N2 + N3 - SHARED;
   C1 v;           // [41] ADMM state
@@ -93,6 +93,7 @@ struct Store {
   C3 H;           // [55]
   C3 lane_inrm;   // [8]
   C3 lov;         // [5]  lower bound of the speed rows (-BIG when dropped)
+  C3 blo, bhi;    // [5]  per-problem box of the accelerations b_i (tightened by the infeasibility screen)
   // sh: this thread's first element of the strided part; lo: thread-private buffer of LOCAL doubles
   MPCB_HD Store(double* sh, double* lo) {
     auto take1 = [&](int n) { C1 c; if (LEVEL >= 1) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
@@ -100,7 +101,7 @@ struct Store {
     auto take3 = [&](int n) { C3 c; if (LEVEL >= 3) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
     v = take1(M_ROWS); rho = take1(M_ROWS); hio = take1(2 * N_OBSROW); D = take1(N_DO); O = take1(N_DO);
     L = take2(NTRI); rdiag = take2(NV); q = take2(NV); lane_c = take2(N_LANE);
-    H = take3(NTRI); lane_inrm = take3(N_LANE); lov = take3(NH);
+    H = take3(NTRI); lane_inrm = take3(N_LANE); lov = take3(NH); blo = take3(NH); bhi = take3(NH);
   }
 };
 
@@ -293,7 +294,10 @@ template <class ST, class F>
 MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const ST& st, const double (&x)[NV], F&& f) {
   const double h = P.h;
 #pragma unroll
-  for (int i = 0; i < NV; ++i) f(i, x[i], P.umin[i & 1], P.umax[i & 1]);
+  for (int i = 0; i < NV; ++i) {
+    if (i & 1) f(i, x[i], st.blo[i >> 1], st.bhi[i >> 1]);
+    else f(i, x[i], P.umin[0], P.umax[0]);
+  }
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
     double dj = 0.0, oj = 0.0;
@@ -559,39 +563,75 @@ struct SolveOut { int status, rounds, iters; bool const_infeasible; };
 
 // Bounds of the rows that are exactly affine in U (speed, obstacle), and a rigorous screen: such a row that
 // cannot be met anywhere inside the control box makes the problem infeasible whatever the other rows do
-// (all coefficients are >= 0, so the row's extreme over the box sits at b = u2_min resp. u2_max).  Those rows
-// are dropped from the QP (the solve then returns the best controls for the remaining rows) and the problem is
-// flagged infeasible at once instead of waiting for an ADMM certificate.  Also: table hints, warm start
+// (all coefficients are >= 0, so the row's extreme over the box sits at b = u2_min resp. u2_max).  Such a row is
+// replaced by what violates it least without fighting the other affine rows: the accelerations it involves are pinned,
+// through their box, to the "stop as fast as possible and stay stopped" profile (what a controller should do when it
+// can no longer keep the gap), and the problem is flagged infeasible at once instead of waiting for an ADMM certificate.  Also: table hints, warm start
 // (trajectory_tracking.py:223-246) clipped to the bounds as scipy does (_slsqp_py.py:322).  Returns "screened".
 template <class ST>
 MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const ST& st) {
   bool screened = false;
+  double blo[NH], bhi[NH], bstop[NH];
+  {
+    // "stop as fast as the box allows and stay stopped" (never asks for a negative speed, so it cannot fight the
+    // v_j >= 0 rows): the acceleration profile that violates an unreachable obstacle row least
+    double vr = pb.x0[4];
 #pragma unroll
-  for (int j = 0; j < NH; ++j) {
-    const double cmax = P.h * (double)(j + 1) * P.umax[1];            // max of v_{j+1} - v0 over the box
-    const bool dead = cmax < -pb.x0[4] - P.feas_tol;
-    st.lov[j] = dead ? -BIG : -pb.x0[4];
-    screened |= dead;
+    for (int i = 0; i < NH; ++i) {
+      blo[i] = P.umin[1]; bhi[i] = P.umax[1];
+      const double b = clipd(-vr / P.h, P.umin[1], P.umax[1]);
+      bstop[i] = b;
+      vr = fma(P.h, b, vr);
+    }
   }
+  // Pinning tightens the box, which can put further rows out of reach: sweep until nothing changes (each sweep pins
+  // at least one more step or stops; 3 sweeps cover the cascades seen, the robust pass catches anything left).
+  bool dead_v[NH], dead_1[2][NH], dead_2[2][NH];
 #pragma unroll
-  for (int k = 0; k < 2; ++k)
+  for (int j = 0; j < NH; ++j) { dead_v[j] = false; dead_1[0][j] = dead_1[1][j] = dead_2[0][j] = dead_2[1][j] = false; }
+  for (int sweep = 0; sweep < 3; ++sweep) {
+    double cum_lo = 0.0, cum_hi = 0.0, s_lo = 0.0;     // extremes over the current box of v_j - v0 and of S_j
 #pragma unroll
     for (int j = 1; j <= NH; ++j) {
-      const double base = (pb.obs[k][0] + pb.obs[k][1] * (j * P.h)) - pb.x0[0] - j * P.h * pb.x0[4];
-      const double smin = P.h * P.h * (double)((j - 1) * j / 2) * P.umin[1];     // min of S_j over the box
-      const double cmin = P.h * (double)j * P.umin[1];                           // min of v_j - v0
-      const double h1 = base - P.obs_safe, h2 = base - P.tgap * pb.x0[4];
-      const bool on = k < pb.n_obs;
-      const bool dead1 = on && (smin > h1 + P.feas_tol);           // j = 1: S_1 == 0, the row is constant in U
-      const bool dead2 = on && (smin + P.tgap * cmin > h2 + P.feas_tol);
-      if (j > 1) st.hio[N_OBSROW * k + (j - 2)] = (!on || dead1) ? BIG : h1;
-      st.hio[N_OBSROW * k + 4 + (j - 1)] = (!on || dead2) ? BIG : h2;
-      screened |= dead1 | dead2;
+      if (j > 1) s_lo = fma(P.h, cum_lo, s_lo);        // S_j = h sum_{m<j} (v_m - v0)
+      cum_lo = fma(P.h, blo[j - 1], cum_lo);
+      cum_hi = fma(P.h, bhi[j - 1], cum_hi);
+      bool pin_to_j = false, pin_to_jm1 = false;
+      if (cum_hi < -pb.x0[4] - P.feas_tol) { dead_v[j - 1] = true; pin_to_j = true; }   // v_j >= 0 out of reach
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        if (k < pb.n_obs) {
+          const double base = (pb.obs[k][0] + pb.obs[k][1] * (j * P.h)) - pb.x0[0] - j * P.h * pb.x0[4];
+          if (s_lo > base - P.obs_safe + P.feas_tol) { dead_1[k][j - 1] = true; pin_to_jm1 = true; }   // j = 1: constant row
+          if (fma(P.tgap, cum_lo, s_lo) > base - P.tgap * pb.x0[4] + P.feas_tol) { dead_2[k][j - 1] = true; pin_to_j = true; }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < NH; ++i)
+        if ((pin_to_j && i < j) || (pin_to_jm1 && i < j - 1)) { blo[i] = bstop[i]; bhi[i] = bstop[i]; }
     }
+  }
+#pragma unroll
+  for (int j = 1; j <= NH; ++j) {
+    st.lov[j - 1] = dead_v[j - 1] ? -BIG : -pb.x0[4];
+    screened |= dead_v[j - 1];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double base = (pb.obs[k][0] + pb.obs[k][1] * (j * P.h)) - pb.x0[0] - j * P.h * pb.x0[4];
+      const bool on = k < pb.n_obs;
+      if (j > 1) st.hio[N_OBSROW * k + (j - 2)] = (!on || dead_1[k][j - 1]) ? BIG : base - P.obs_safe;
+      st.hio[N_OBSROW * k + 4 + (j - 1)] = (!on || dead_2[k][j - 1]) ? BIG : base - P.tgap * pb.x0[4];
+      screened |= on && (dead_1[k][j - 1] || dead_2[k][j - 1]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NH; ++i) { st.blo[i] = blo[i]; st.bhi[i] = bhi[i]; }
   warm_start(T, P, pb.x0, pb.obs, pb.n_obs, pb.U, pb.hint);
   pb.hint[NH] = pb.hint[NH - 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) pb.U[i] = clipd(pb.U[i], P.umin[i & 1], P.umax[i & 1]);  // scipy clips x0 to the bounds
+#pragma unroll
+  for (int i = 0; i < NH; ++i) pb.U[2 * i + 1] = clipd(pb.U[2 * i + 1], blo[i], bhi[i]);
   return screened;
 }
 
@@ -673,7 +713,9 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
                                                                       // 2 through the final constraint check)
     }
   }
-  if (infeasible) out.status = 2;
+  // an infeasibility verdict is final only on a point the pass actually converged to (or, in the robust pass, gave
+  // up on): a first pass that could not close its QP hands the problem over whatever the screens said
+  if (infeasible && (!FIRST_PASS || out.status == 0)) out.status = 2;
   // the returned controls always respect the box (a no-op for converged problems; non-converged or infeasible
   // ADMM iterates may sit slightly outside).  SLSQP treats the bounds as hard in the same way.
 #pragma unroll

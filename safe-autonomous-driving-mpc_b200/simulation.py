@@ -1,0 +1,84 @@
+"""Batched closed loop on the GPU: host mirror of ``run_simulation`` (trajectory_tracking.py:377-443)
+for B vehicles at once.  The loop body -- ObstaclesFSM.update, solve, Euler plant step, stop test -- runs as device
+kernels behind ``mpcb_sim_*``; the host only decides how many steps to enqueue and when to look."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import Scenario, check
+
+
+def _dp(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def make_scenario(which=2, **over):
+    """Scenario constants: which=2 as committed (:294-308), which=3 the commented trajectory3 block (:313-327)."""
+    s = Scenario()
+    check(_lib.load().mpcb_scenario_default(C.byref(s), int(which)))
+    for k, v in over.items():
+        if not hasattr(s, k):
+            raise TypeError(f"unknown scenario field {k!r}")
+        setattr(s, k, v)
+    return s
+
+
+class BatchedSimulation:
+    def __init__(self, tracker, scenarios, B=None, x_init=None, history_steps=0):
+        """tracker: BatchedTracker; scenarios: one Scenario (shared) or a list of B; x_init: [B,5] or None for the
+        reference's start state."""
+        self._lib = tracker._lib
+        self._t = tracker
+        scen = list(scenarios) if isinstance(scenarios, (list, tuple)) else [scenarios]
+        if B is None:
+            B = len(scen) if len(scen) > 1 else (len(x_init) if x_init is not None else 1)
+        arr = (Scenario * len(scen))(*scen)
+        xi = None
+        if x_init is not None:
+            xi = np.ascontiguousarray(x_init, dtype=np.float64).reshape(B, 5)
+        h = C.c_void_p()
+        check(self._lib.mpcb_sim_create(C.byref(h), tracker._need(), int(B), arr, len(scen),
+                                        _dp(xi) if xi is not None else None, int(history_steps)), "mpcb_sim_create")
+        self._h = h
+        self.B = int(B)
+        self.history_steps = int(history_steps)
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._lib.mpcb_sim_destroy(h)
+            self._h = None
+
+    def step(self, n=1, stream=None):
+        check(self._lib.mpcb_sim_step(self._h, int(n), C.c_void_p(stream or 0)), "mpcb_sim_step")
+
+    def alive(self):
+        n = C.c_int()
+        check(self._lib.mpcb_sim_alive(self._h, C.byref(n), None))
+        return n.value
+
+    def state(self):
+        x = np.empty((self.B, 5)); st = np.empty(self.B, np.int32); nu = np.empty(self.B, np.int32)
+        check(self._lib.mpcb_sim_state(self._h, _dp(x), _dp(st), _dp(nu), None))
+        return x, st, nu
+
+    def history(self):
+        n = C.c_int()
+        check(self._lib.mpcb_sim_history(self._h, C.byref(n), None, None, None, None, None, None))
+        T, B = n.value, self.B
+        hx = np.empty((T, B, 5)); hu = np.empty((T, B, 2)); ho = np.empty((T, B))
+        hs = np.empty((T, B), np.int32); ht = np.empty((T, B), np.int32)
+        check(self._lib.mpcb_sim_history(self._h, C.byref(n), _dp(hx), _dp(hu), _dp(ho), _dp(hs), _dp(ht), None))
+        return dict(x=hx, u=hu, obs_s=ho, status=hs, tl=ht)
+
+    def run(self, max_steps=200000, check_every=64):
+        """Drive until every vehicle has passed s_max - 1 (or max_steps).  Returns the number of steps enqueued."""
+        done = 0
+        while done < max_steps:
+            k = min(check_every, max_steps - done)
+            self.step(k)
+            done += k
+            if self.alive() == 0:
+                break
+        return done

@@ -1,0 +1,82 @@
+"""GPU tests of the batched closed loop on the device (mpcb_sim_*)."""
+import numpy as np
+import pytest
+
+from conftest import golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _scenario(M, i):
+    if i == 1:
+        return M.make_scenario(2, dynamic_obstacle=0, traffic_light=0)
+    return M.make_scenario(i)
+
+
+@pytest.mark.parametrize("i", [1, 2, 3])
+def test_device_loop_matches_host_driven_loop(i, gpu_trackers):
+    """The device loop (FSM kernel -> solve -> plant kernel) against the reference-shaped host loop that calls the same
+    solver once per step (environment.run_simulation): same step count, same obstacle log, states equal to rounding."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from safe_autonomous_driving_mpc_b200 import environment as E
+    L, T = gpu_trackers[i]
+    sc = {1: None, 2: E.SCENARIO_TRAJECTORY2, 3: E.SCENARIO_TRAJECTORY3}[i]
+    fsm = M.ObstaclesFSM(dynamic_obstacle=i > 1, traffic_light=i > 1, scenario=sc)
+    flags = []
+    hx, hu, ht, hp, hobs, htl, _ = M.run_simulation(T, fsm, L, record_flags=flags)
+    sim = M.BatchedSimulation(T, _scenario(M, i), B=1, history_steps=len(hu) + 64)
+    n = sim.run(max_steps=len(hu) + 64, check_every=32)
+    x, steps, unsolved = sim.state()
+    assert steps[0] == len(hu), (steps[0], len(hu))
+    assert n >= steps[0] and sim.alive() == 0
+    h = sim.history()
+    k = steps[0]
+    assert np.all(h["status"][k:, 0] == -1)                                   # frozen after arrival
+    assert np.abs(h["x"][:k, 0] - hx[:-1]).max() <= 1e-7
+    assert np.abs(x[0] - hx[-1]).max() <= 1e-7
+    assert np.abs(h["u"][:k, 0] - hu).max() <= 1e-6
+    obs_ref = np.array(hobs, dtype=np.float64)
+    assert np.array_equal(np.isnan(h["obs_s"][:k, 0]), np.isnan(obs_ref))
+    assert np.nanmax(np.abs(h["obs_s"][:k, 0] - obs_ref), initial=0.0) <= 1e-9
+    assert [("GREEN" if t else "RED") for t in h["tl"][:k, 0]] == list(htl)
+    assert unsolved[0] == sum(1 for f in flags if f[0] != 0)
+    # same verdict data as the reference run (step count of the as-shipped reference within 1 %)
+    z = golden(f"closed_loop_traj{i}")
+    assert abs(k - len(z["hist_u"])) <= max(2, int(0.01 * len(z["hist_u"])))
+
+
+def test_many_vehicles_monte_carlo(gpu_trackers):
+    """256 vehicles on trajectory2 with perturbed starts and per-vehicle scenario constants: copies of the same vehicle
+    are bitwise identical, every vehicle arrives, nobody collides with the car or runs the red light."""
+    import safe_autonomous_driving_mpc_b200 as M
+    L, T = gpu_trackers[2]
+    rng = np.random.default_rng(11)
+    B = 256
+    x_init = np.tile([0.0, 0.0, 0.0, 0.0, 0.5], (B, 1))
+    x_init[8:, 1] += rng.normal(0, 0.05, B - 8)
+    x_init[8:, 4] += rng.uniform(0, 3.0, B - 8)
+    scen = []
+    for b in range(B):
+        if b < 8:
+            scen.append(M.make_scenario(2))
+        else:
+            scen.append(M.make_scenario(2, obs_v=float(rng.uniform(3.0, 6.0)), tl_pos=float(rng.uniform(450.0, 650.0)),
+                                        tl_stop_duration=float(rng.uniform(5.0, 25.0))))
+    sim = M.BatchedSimulation(T, scen, B=B, x_init=x_init, history_steps=3000)
+    sim.run(max_steps=3000, check_every=100)
+    assert sim.alive() == 0
+    x, steps, unsolved = sim.state()
+    h = sim.history()
+    assert np.all(x[:, 0] > L.s_max - 1.0) and np.all(np.isfinite(x))
+    for b in range(1, 8):
+        assert steps[b] == steps[0]
+        assert np.array_equal(h["x"][:, b], h["x"][:, 0], equal_nan=True)
+    # safety verdicts per vehicle (sanity_checks.py:141-176): gap to the car >= 1 m, red light not run
+    for b in range(B):
+        k = steps[b]
+        gap = h["obs_s"][:k, b] - h["x"][:k, b, 0]
+        assert np.nanmin(np.where(gap > -50.0, gap, np.nan), initial=np.inf) >= 1.0
+        red = h["tl"][:k, b] == 0
+        tl_pos = scen[b].tl_pos
+        assert np.all(h["x"][:k, b, 0][red] <= tl_pos + 1e-9)
+    assert (unsolved / np.maximum(steps, 1)).mean() < 0.1
