@@ -22,11 +22,11 @@ namespace mpcb {
 #ifndef MPCB_SOLVE_CTAS
 #define MPCB_SOLVE_CTAS 2          // CTAs per SM the kernel is compiled for
 #endif
-#ifndef MPCB_STORE_LEVEL
-#define MPCB_STORE_LEVEL 0         // how much of the per-thread working set sits in shared memory (mpcb_solver.cuh)
+#ifndef MPCB_STORE_MASK
+#define MPCB_STORE_MASK 7          // which per-thread arrays sit in shared memory (mpcb_solver.cuh): v, rho, hio
 #endif
 constexpr int SOLVE_THREADS = MPCB_SOLVE_THREADS;
-using SolveStore = Store<(MPCB_STORE_LEVEL > 0 ? SOLVE_THREADS : 1), MPCB_STORE_LEVEL>;
+using SolveStore = Store<(MPCB_STORE_MASK != 0 ? SOLVE_THREADS : 1), MPCB_STORE_MASK>;
 constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::SHARED * SOLVE_THREADS;
 constexpr int EVAL_THREADS = 128;
 
@@ -226,7 +226,7 @@ mpcb_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
     pb.obs[0][0] = pb.obs[0][1] = pb.obs[1][0] = pb.obs[1][1] = 0.0;
 #pragma unroll
     for (int j = 0; j <= NH; ++j) pb.hint[j] = 1;
-    typedef Store<1, 0> EvalStore;
+    typedef Store<1, 0u> EvalStore;
     double buf[EvalStore::LOCAL];
     const EvalStore st(nullptr, buf);
     double cv;
@@ -406,13 +406,17 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   if ((e = cudaMemcpy(c->d_s, t->s.data(), sizeof(double) * K, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
   if ((e = cudaMemcpy(c->d_y, t->y.data(), sizeof(double) * K * 4, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
   if ((e = cudaMemcpy(c->d_u, t->u.data(), sizeof(double) * c->Ku * 2, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
-  if ((e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate"));
+  // streams of the host-buffer entry point: part c of a large batch runs on xs[c] with a priority that falls with c,
+  // so the parts drain in order and the D2H copy of one overlaps the kernels of the next
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);          // hi is numerically smaller
+  if ((e = cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi)) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate"));
   if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev_mid)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   c->xs[0] = c->stream;
   for (int k = 1; k < 4; ++k) {
-    if ((e = cudaStreamCreateWithFlags(&c->xs[k], cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate"));
+    if ((e = cudaStreamCreateWithPriority(&c->xs[k], cudaStreamNonBlocking, std::min(prio_lo, prio_hi + k))) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate"));
     if ((e = cudaEventCreateWithFlags(&c->xe[k], cudaEventDisableTiming)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   }
   c->dt.s = c->d_s; c->dt.y = c->d_y; c->dt.u = c->d_u;
@@ -492,7 +496,7 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
     } else {
       // thread per problem; CTAs beyond the list length exit at once (one warp per CTA when the working set is
       // thread-local: the few leftover warps then never wait for each other)
-      const int t2 = (MPCB_STORE_LEVEL == 0) ? 32 : SOLVE_THREADS;
+      const int t2 = (MPCB_STORE_MASK == 0) ? 32 : SOLVE_THREADS;
       mpcb_solve_kernel<false><<<(B + t2 - 1) / t2, t2, SOLVE_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv,
                                                                          n_obs, U_out, Xpred_out, obj_out, status_out,
                                                                          iters_out, cmin_out, active_out, nullptr, nullptr);

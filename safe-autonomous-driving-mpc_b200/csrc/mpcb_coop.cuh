@@ -20,7 +20,7 @@ constexpr int CW_K = 2;                 // rows per lane
 constexpr int CW_ROWS = 32 * CW_K;      // padded row count (rows >= M_ROWS are null)
 
 struct WarpShared {
-  double buf[Store<1, 0>::LOCAL];       // lane 0's thread-level store (H, q, D, O, lane_c, ...)
+  double buf[Store<1, 0u>::LOCAL];       // lane 0's thread-level store (H, q, D, O, lane_c, ...)
   Problem pb;
   double A[CW_ROWS][NV + 1];            // dense rows (+1 pad: conflict-free column reads)
   double rho[CW_ROWS];
@@ -44,7 +44,7 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 // dense coefficients, bounds and 1/|a|^2 of row r at the current linearisation (same rows as for_rows)
-__device__ __forceinline__ void coop_row(const DevParams& P, const Store<1, 0>& st, const Problem& pb, int r,
+__device__ __forceinline__ void coop_row(const DevParams& P, const Store<1, 0u>& st, const Problem& pb, int r,
                                          double (&a)[NV], double& lo, double& hi, double& inrm, bool& exists) {
   const double h = P.h;
 #pragma unroll
@@ -86,7 +86,7 @@ __device__ __forceinline__ void coop_row(const DevParams& P, const Store<1, 0>& 
 template <bool FIRST_PASS>
 __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared& ws, int lane) {
   const unsigned FULL = 0xffffffffu;
-  const Store<1, 0> st(nullptr, ws.buf);
+  const Store<1, 0u> st(nullptr, ws.buf);
   Problem& pb = ws.pb;
   const Policy& pl = P.pol[FIRST_PASS ? 1 : 0];
   SolveOut out{MPCB_MAXITER, 0, 0, false};

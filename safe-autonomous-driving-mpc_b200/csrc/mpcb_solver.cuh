@@ -66,42 +66,48 @@ struct LCol {          // thread-private, plain: registers / local memory, place
 template <bool SHARED, int S> struct ColSel { typedef Col<S> type; };
 template <int S> struct ColSel<false, S> { typedef LCol type; };
 
-// Per-thread working set.  LEVEL says how much of it sits in the strided (shared-memory) part:
-//   0  nothing (S must be 1: host build, evaluation kernel)
-//   1  row vectors v, rho, obstacle bounds, lane sensitivities D, O                    (140 doubles)
-//   2  + Cholesky factor L, its reciprocal diagonal, q, lane offsets                    (223 doubles)
-//   3  + H, lane row norms, speed-row bounds                                            (291 doubles)
-// the rest lives in a thread-private buffer of LOCAL doubles.
-template <int S, int LEVEL>
+// Per-thread working set.  MASK says which array groups sit in the strided (shared-memory) part, the rest lives in
+// a thread-private buffer of LOCAL doubles (registers / local memory, placement left to the compiler):
+//   bit 0  v        [41] ADMM state                      bit 4  L, rdiag   [55+10] factor of K
+//   bit 1  rho      [41] step sizes                      bit 5  q, lane_c  [10+8]
+//   bit 2  hio      [18] obstacle-row bounds             bit 6  H          [55]
+//   bit 3  D, O     [20+20] lane sensitivities           bit 7  lane_inrm, lov, blo, bhi  [8+5+5+5]
+// MASK = 0: host build, evaluation kernel, cooperative kernel (S must be 1).
+template <int S, unsigned MASK>
 struct Store {
-  typedef typename ColSel<(LEVEL >= 1), S>::type C1;
-  typedef typename ColSel<(LEVEL >= 2), S>::type C2;
-  typedef typename ColSel<(LEVEL >= 3), S>::type C3;
-  static constexpr int N1 = 2 * M_ROWS + 2 * N_OBSROW + 2 * N_DO;     // 140
-  static constexpr int N2 = NTRI + NV + NV + N_LANE;                  // 83
-  static constexpr int N3 = NTRI + N_LANE + NH + 2 * NH;              // 78
-  static constexpr int SHARED = (LEVEL >= 1 ? N1 : 0) + (LEVEL >= 2 ? N2 : 0) + (LEVEL >= 3 ? N3 : 0);
-  static constexpr int LOCAL = N1 + N2 + N3 - SHARED;
-  C1 v;           // [41] ADMM state
-  C1 rho;         // [41] step sizes of the current factorisation
-  C1 hio;         // [18] upper bounds of the obstacle rows (BIG: row absent or dropped)
-  C1 D, O;        // [20] lane sensitivities
-  C2 L;           // [55] factor of K
-  C2 rdiag;       // [10]
-  C2 q;           // [10]
-  C2 lane_c;      // [8]  row value offset: (d_j + alpha o_j)(U) - a.U
-  C3 H;           // [55]
-  C3 lane_inrm;   // [8]
-  C3 lov;         // [5]  lower bound of the speed rows (-BIG when dropped)
-  C3 blo, bhi;    // [5]  per-problem box of the accelerations b_i (tightened by the infeasibility screen)
+  template <int BIT> using G = typename ColSel<((MASK >> BIT) & 1u) != 0, S>::type;
+  static constexpr int size_of(int bit) {
+    return bit == 0 ? M_ROWS : bit == 1 ? M_ROWS : bit == 2 ? 2 * N_OBSROW : bit == 3 ? 2 * N_DO : bit == 4 ? NTRI + NV
+         : bit == 5 ? NV + N_LANE : bit == 6 ? NTRI : N_LANE + 3 * NH;
+  }
+  static constexpr int shared_doubles() {
+    int n = 0;
+    for (int b = 0; b < 8; ++b) if ((MASK >> b) & 1u) n += size_of(b);
+    return n;
+  }
+  static constexpr int TOTAL = 2 * M_ROWS + 2 * N_OBSROW + 2 * N_DO + NTRI + NV + NV + N_LANE + NTRI + N_LANE + 3 * NH;
+  static constexpr int SHARED = shared_doubles();
+  static constexpr int LOCAL = TOTAL - SHARED;
+  G<0> v;
+  G<1> rho;
+  G<2> hio;         // upper bounds of the obstacle rows (BIG: row absent or dropped)
+  G<3> D, O;
+  G<4> L, rdiag;
+  G<5> q, lane_c;   // lane_c: row value offset (d_j + alpha o_j)(U) - a.U
+  G<6> H;
+  G<7> lane_inrm, lov, blo, bhi;   // lov: lower bound of the speed rows; blo/bhi: per-problem box of the accelerations
   // sh: this thread's first element of the strided part; lo: thread-private buffer of LOCAL doubles
   MPCB_HD Store(double* sh, double* lo) {
-    auto take1 = [&](int n) { C1 c; if (LEVEL >= 1) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
-    auto take2 = [&](int n) { C2 c; if (LEVEL >= 2) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
-    auto take3 = [&](int n) { C3 c; if (LEVEL >= 3) { c.p = (decltype(c.p))sh; sh += n * S; } else { c.p = (decltype(c.p))lo; lo += n; } return c; };
-    v = take1(M_ROWS); rho = take1(M_ROWS); hio = take1(2 * N_OBSROW); D = take1(N_DO); O = take1(N_DO);
-    L = take2(NTRI); rdiag = take2(NV); q = take2(NV); lane_c = take2(N_LANE);
-    H = take3(NTRI); lane_inrm = take3(N_LANE); lov = take3(NH); blo = take3(NH); bhi = take3(NH);
+    auto take = [&](auto& c, bool shared, int n) {
+      typedef decltype(c.p) P;
+      if (shared) { c.p = (P)sh; sh += n * S; } else { c.p = (P)lo; lo += n; }
+    };
+    take(v, MASK & 1u, M_ROWS); take(rho, MASK & 2u, M_ROWS); take(hio, MASK & 4u, 2 * N_OBSROW);
+    take(D, MASK & 8u, N_DO); take(O, MASK & 8u, N_DO);
+    take(L, MASK & 16u, NTRI); take(rdiag, MASK & 16u, NV);
+    take(q, MASK & 32u, NV); take(lane_c, MASK & 32u, N_LANE);
+    take(H, MASK & 64u, NTRI);
+    take(lane_inrm, MASK & 128u, N_LANE); take(lov, MASK & 128u, NH); take(blo, MASK & 128u, NH); take(bhi, MASK & 128u, NH);
   }
 };
 

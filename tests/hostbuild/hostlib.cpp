@@ -80,7 +80,7 @@ int host_solve_batch(const double* s, const double* y, const double* u, int K, i
       for (int c = 0; c < 5; ++c) pb.x0[c] = x0[5 * b + c];
       for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[4 * b + 2 * k]; pb.obs[k][1] = obs_sv[4 * b + 2 * k + 1]; }
       pb.n_obs = std::min(std::max(n_obs[b], 0), 2);
-      typedef Store<1, 0> HostStore;
+      typedef Store<1, 0u> HostStore;
       double buf[HostStore::LOCAL];
       HostStore st(nullptr, buf);
       SolveOut so = (pass == 1) ? solve_one<true>(T, P, pb, st, true) : solve_one<false>(T, P, pb, st, true);

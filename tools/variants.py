@@ -6,20 +6,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
-    "T64_C3_L1": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=1"],
-    "T64_C2_L2": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_LEVEL=2"],
-    "T64_C4_L0": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_LEVEL=0"],
-    "T128_C2_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_LEVEL=0"],
-    "T256_C1_L0": ["MPCB_SOLVE_THREADS=256", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_LEVEL=0"],
-    "T192_C1_L0": ["MPCB_SOLVE_THREADS=192", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_LEVEL=0"],
-    "T128_C1_L1": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_LEVEL=1"],
-    "T128_C3_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=0"],
-    "T128_C4_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_LEVEL=0"],
-    "T256_C2_L0": ["MPCB_SOLVE_THREADS=256", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_LEVEL=0"],
-    "T128_C6_L0": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=6", "MPCB_STORE_LEVEL=0"],
-    "T32_C6_L1": ["MPCB_SOLVE_THREADS=32", "MPCB_SOLVE_CTAS=6", "MPCB_STORE_LEVEL=1"],
-    "T32_C3_L3": ["MPCB_SOLVE_THREADS=32", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=3"],
-    "T32_C4_L2": ["MPCB_SOLVE_THREADS=32", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_LEVEL=2"],
+    "T128_C2_M3": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=3"],      # v rho
+    "T128_C2_M7": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7"],      # v rho hio
+    "T128_C2_M35": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=35"],    # v rho q lane_c
+    "T128_C2_M13": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=13"],    # v hio D O
+    "T128_C2_M18": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=18"],    # rho L
+    "T128_C2_M1": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=1"],      # v
+    "T128_C2_M9": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=9"],      # v D O
+    "T96_C2_M15": ["MPCB_SOLVE_THREADS=96", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=15"],      # v rho hio D O (140)
 }
 if sys.argv[1] == "build":
     import importlib
