@@ -226,6 +226,12 @@ int mpcb_sim_state(mpcb_sim_handle s, double* x, int* steps, int* n_unsolved, vo
 int mpcb_sim_history(mpcb_sim_handle s, int* n_recorded, double* hist_x, double* hist_u, double* hist_obs,
                      int* hist_status, int* hist_tl, void* cuda_stream);
 
+/* trajectory_tracking_check (sanity_checks.py:79-184) for every vehicle on the recorded history (needs history_steps > 0).
+ * verdict [B] HOST: bit 0 destination reached, 1 stayed on road (|d| <= 1.5), 2 steering within limits, 3 acceleration
+ * within limits (+-0.1), 4 moving obstacle avoided (gap >= 1 m), 5 red light respected, 6 history covers the whole drive
+ * (1 = passed).  metrics [B][4] HOST (may be NULL): max |d|, min gap to the car (1e30 if never present), final s, steps. */
+int mpcb_sim_check(mpcb_sim_handle s, int* verdict, double* metrics, void* cuda_stream);
+
 const char* mpcb_strerror(int code);
 const char* mpcb_last_cuda_error(void);
 int mpcb_abi_version(void);

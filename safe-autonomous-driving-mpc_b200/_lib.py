@@ -93,6 +93,7 @@ SYMBOLS = {
     "mpcb_sim_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "mpcb_sim_alive": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "mpcb_sim_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpcb_sim_check": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpcb_sim_history": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)] + [C.c_void_p] * 5 + [C.c_void_p]),
     "mpcb_strerror": (C.c_char_p, [C.c_int]),
     "mpcb_last_cuda_error": (C.c_char_p, []),

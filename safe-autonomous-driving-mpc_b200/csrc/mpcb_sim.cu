@@ -119,6 +119,52 @@ __global__ void mpcb_count_alive_kernel(int B, double s_stop, const double* __re
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
 }
 
+// trajectory_tracking_check (sanity_checks.py:79-184) for every vehicle at once, on the recorded histories; one thread
+// per vehicle, coalesced over vehicles.  Verdict bits (1 = passed): 0 destination reached (:98-103), 1 stayed on road
+// (:106-111), 2 steering within limits +-0.1 (:121-125), 3 acceleration within limits (:127-131), 4 moving obstacle
+// avoided, gap >= 1 m (:142-164), 5 red light respected (:167-181), 6 history covers the whole drive.
+// (The reference's CPU-time item :134-139 is a property of the host, not of the trajectory; it is not evaluated here.)
+__global__ void __launch_bounds__(128)
+mpcb_sim_check_kernel(int B, int n_rec, double s_total, double u1_min, double u1_max, double u2_min, double u2_max,
+                      const double* __restrict__ x_final, const int* __restrict__ steps,
+                      const DevScenario* __restrict__ scen, const double* __restrict__ hist_x,
+                      const double* __restrict__ hist_u, const double* __restrict__ hist_obs,
+                      const int* __restrict__ hist_tl, int* __restrict__ verdict, double* __restrict__ metrics) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const DevScenario sc = scen[b];
+  const int n = min(steps[b], n_rec);
+  const double tol = 0.1, lateral = 1.5, safety = 1.0;
+  double max_dev = fabs(x_final[(size_t)b * 5 + 1]);
+  double u1lo = BIG, u1hi = -BIG, u2lo = BIG, u2hi = -BIG, min_gap = BIG;
+  int first_pass = -1;
+  for (int t = 0; t < n; ++t) {
+    const size_t i = (size_t)t * B + b;
+    const double s = hist_x[i * 5], d = hist_x[i * 5 + 1];
+    max_dev = fmax(max_dev, fabs(d));
+    const double a = hist_u[i * 2], c = hist_u[i * 2 + 1];
+    u1lo = fmin(u1lo, a); u1hi = fmax(u1hi, a); u2lo = fmin(u2lo, c); u2hi = fmax(u2hi, c);
+    const double os = hist_obs[i];
+    if (!isnan(os)) min_gap = fmin(min_gap, os - s);
+    if (first_pass < 0 && s > sc.tl_pos) first_pass = t;
+  }
+  const double s_final = x_final[(size_t)b * 5];
+  int v = 0;
+  if (!(s_final < s_total - 1.0)) v |= 1;
+  if (!(max_dev > lateral)) v |= 2;
+  if (!(u1lo < u1_min - tol || u1hi > u1_max + tol)) v |= 4;
+  if (!(u2lo < u2_min - tol || u2hi > u2_max + tol)) v |= 8;
+  if (!(sc.dynamic_obstacle && min_gap < safety)) v |= 16;
+  const bool ran_red = sc.traffic_light && first_pass >= 0 && hist_tl[(size_t)first_pass * B + b] == 0;
+  if (!ran_red) v |= 32;
+  if (steps[b] <= n_rec) v |= 64;
+  verdict[b] = v;
+  metrics[(size_t)b * 4 + 0] = max_dev;
+  metrics[(size_t)b * 4 + 1] = min_gap;
+  metrics[(size_t)b * 4 + 2] = s_final;
+  metrics[(size_t)b * 4 + 3] = (double)steps[b];
+}
+
 }  // namespace mpcb
 
 using namespace mpcb;
@@ -249,6 +295,30 @@ int mpcb_sim_state(mpcb_sim_handle s, double* x, int* steps, int* n_unsolved, vo
   if (steps) CK(cudaMemcpyAsync(steps, s->steps, nb * 4, cudaMemcpyDeviceToHost, st));
   if (n_unsolved) CK(cudaMemcpyAsync(n_unsolved, s->n_unsolved, nb * 4, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
+  return MPCB_OK;
+}
+
+int mpcb_sim_check(mpcb_sim_handle s, int* verdict, double* metrics, void* cuda_stream) {
+  if (!s || !verdict || s->cap < 1) return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(s->h->device));
+  cudaStream_t st = (cudaStream_t)cuda_stream;
+  const size_t nb = (size_t)s->B;
+  int* d_v = nullptr;
+  double* d_m = nullptr;
+  CK(cudaMalloc((void**)&d_v, nb * 4));
+  if (cudaMalloc((void**)&d_m, nb * 32) != cudaSuccess) { cudaFree(d_v); cudaGetLastError(); return MPCB_ERR_NOMEM; }
+  const mpcb_params& p = s->h->params;
+  const int nt = s->t < s->cap ? s->t : s->cap;
+  mpcb_sim_check_kernel<<<(s->B + 127) / 128, 128, 0, st>>>(s->B, nt, s->h->dt.s_max, p.u_min[0], p.u_max[0], p.u_min[1],
+                                                           p.u_max[1], s->x, s->steps, s->scen, s->hist_x, s->hist_u,
+                                                           s->hist_obs, s->hist_tl, d_v, d_m);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaMemcpyAsync(verdict, d_v, nb * 4, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess && metrics) e = cudaMemcpyAsync(metrics, d_m, nb * 32, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d_v); cudaFree(d_m);
+  if (e != cudaSuccess) return cuda_fail(e, "mpcb_sim_check");
+  s->h->launches += 1;
   return MPCB_OK;
 }
 

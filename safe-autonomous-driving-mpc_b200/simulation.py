@@ -72,6 +72,18 @@ class BatchedSimulation:
         check(self._lib.mpcb_sim_history(self._h, C.byref(n), _dp(hx), _dp(hu), _dp(ho), _dp(hs), _dp(ht), None))
         return dict(x=hx, u=hu, obs_s=ho, status=hs, tl=ht)
 
+    CHECKS = ("destination", "on_road", "steering", "acceleration", "obstacle", "light", "history_complete")
+
+    def check(self):
+        """trajectory_tracking_check (sanity_checks.py:79-184) per vehicle: dict of bool arrays [B] plus metrics."""
+        v = np.empty(self.B, np.int32)
+        m = np.empty((self.B, 4))
+        check(self._lib.mpcb_sim_check(self._h, _dp(v), _dp(m), None), "mpcb_sim_check")
+        out = {name: ((v >> k) & 1).astype(bool) for k, name in enumerate(self.CHECKS)}
+        out["passed"] = (v & 63) == 63
+        out.update(max_dev=m[:, 0], min_gap=m[:, 1], s_final=m[:, 2], steps=m[:, 3].astype(np.int64))
+        return out
+
     def run(self, max_steps=200000, check_every=64):
         """Drive until every vehicle has passed s_max - 1 (or max_steps).  Returns the number of steps enqueued."""
         done = 0

@@ -40,6 +40,10 @@ def test_device_loop_matches_host_driven_loop(i, gpu_trackers):
     assert np.nanmax(np.abs(h["obs_s"][:k, 0] - obs_ref), initial=0.0) <= 1e-9
     assert [("GREEN" if t else "RED") for t in h["tl"][:k, 0]] == list(htl)
     assert unsolved[0] == sum(1 for f in flags if f[0] != 0)
+    # vectorised sanity checks == the reference's verdicts on its own run (all items pass, sanity_checks.py:79-184)
+    c = sim.check()
+    assert c["passed"][0] and c["history_complete"][0] and c["steps"][0] == k
+    assert abs(c["max_dev"][0] - np.abs(np.vstack([h["x"][:k, 0], x[:1]])[:, 1]).max()) == 0.0
     # same verdict data as the reference run (step count of the as-shipped reference within 1 %)
     z = golden(f"closed_loop_traj{i}")
     assert abs(k - len(z["hist_u"])) <= max(2, int(0.01 * len(z["hist_u"])))
@@ -80,3 +84,20 @@ def test_many_vehicles_monte_carlo(gpu_trackers):
         tl_pos = scen[b].tl_pos
         assert np.all(h["x"][:k, b, 0][red] <= tl_pos + 1e-9)
     assert (unsolved / np.maximum(steps, 1)).mean() < 0.1
+    # the device check against a numpy restatement of sanity_checks.py:79-184 on the same histories
+    c = sim.check()
+    for b in range(B):
+        k = steps[b]
+        hx = np.vstack([h["x"][:k, b], x[b:b + 1]])
+        hu = h["u"][:k, b]
+        ref = dict(destination=not (hx[-1, 0] < L.s_max - 1.0), on_road=not (np.abs(hx[:, 1]).max() > 1.5),
+                   steering=not (hu[:, 0].min() < -0.6 - 0.1 or hu[:, 0].max() > 0.6 + 0.1),
+                   acceleration=not (hu[:, 1].min() < -5.0 - 0.1 or hu[:, 1].max() > 4.0 + 0.1))
+        os_ = h["obs_s"][:k, b]
+        m = ~np.isnan(os_)
+        ref["obstacle"] = not (m.any() and (os_[m] - hx[:k, 0][m]).min() < 1.0)
+        idx = np.where(hx[:, 0] > scen[b].tl_pos)[0]
+        ref["light"] = not (len(idx) > 0 and idx[0] < k and h["tl"][idx[0], b] == 0)
+        for name, val in ref.items():
+            assert bool(c[name][b]) == val, (b, name)
+    assert c["passed"].all() and c["history_complete"].all()
