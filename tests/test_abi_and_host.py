@@ -113,3 +113,15 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("converged-oracle", ""), f"{f} mentions oracle/"
+
+
+def test_integration_stub_struct_matches_library():
+    """the ctypes mirror printed in INTEGRATION.md must stay in step with struct mpcb_params"""
+    import re
+    from safe_autonomous_driving_mpc_b200 import _lib
+    src = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    m = re.search(r"class Params\(C\.Structure\):.*?\n\n", src, re.S)
+    ns = {"C": C}
+    exec(m.group(0), ns)
+    assert C.sizeof(ns["Params"]) == _lib.load().mpcb_sizeof_params()
+    assert [f[0] for f in ns["Params"]._fields_] == [f[0] for f in _lib.Params._fields_]
