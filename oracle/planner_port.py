@@ -163,3 +163,45 @@ def ctrl_rows(z, N):
     for k in range(N):
         out[k] = [U[k, 0] - U_MIN[0], U_MAX[0] - U[k, 0], U[k, 1] - U_MIN[1], U_MAX[1] - U[k, 1], S[k]]
     return out
+
+
+class OracleEvaluator:
+    """CPU stand-in for PlannerEvaluator.evaluate_host built from the functions above (values) and complex-step
+    derivatives.  TEST INFRASTRUCTURE: lets tests drive ``planner_driver`` without a GPU and check the GPU evaluator
+    against it."""
+
+    def __init__(self, tab, N, dt=DT, simpson_sign=-1, s_total=None, v_min=0.0, v_max=None):
+        self.tab, self.N, self.dt, self.sign = tab, int(N), dt, simpson_sign
+        self.s_total = float(tab.s_max if s_total is None else s_total)
+        self.v_min = v_min
+        self.v_max = float(tab.X[:, 4].max() if v_max is None else v_max)
+
+    def evaluate_host(self, z, lam=None, s0=None, want_jac=True, want_hess=False):
+        z = np.atleast_2d(np.asarray(z, dtype=np.float64))
+        C, N = z.shape[0], self.N
+        s0 = z[:, 0] if s0 is None else np.asarray(s0, dtype=np.float64).reshape(C)
+        out = dict(defect=np.zeros((C, N, 5)), node_rows=np.zeros((C, N + 1, 6)), ctrl_rows=np.zeros((C, N, 5)),
+                   cost_terms=np.zeros((C, N)), cost=np.zeros(C), cost_grad=np.zeros((C, 8 * N + 5)))
+        if want_jac:
+            out["jac"] = np.zeros((C, N, 5, 12))
+        for c in range(C):
+            X, U, S = unpack(z[c], N)
+            out["defect"][c] = defects(self.tab, z[c], N, self.dt, self.sign)
+            out["node_rows"][c] = node_rows(z[c], N, self.v_min, self.v_max)
+            out["ctrl_rows"][c] = ctrl_rows(z[c], N)
+            x0 = np.array([s0[c], 0, 0, 0, 0.0])
+            out["cost_terms"][c] = stage_costs(z[c], N, x0, self.s_total)
+            out["cost"][c] = cost(z[c], N, x0, self.s_total)
+            denom = max(1, self.s_total - s0[c])
+            g = out["cost_grad"][c]
+            for k in range(N):
+                g[5 * k] = -2.0 * W_S * ((self.s_total - X[k, 0]) / denom) / denom
+                g[5 * k + 1] = 2.0 * W_Y * X[k, 1]
+                g[5 * k + 2] = 2.0 * W_Y * X[k, 2]
+                g[5 * (N + 1) + 2 * k] = 2.0 * W_U * U[k, 0]
+                g[5 * (N + 1) + 2 * k + 1] = 2.0 * W_U * U[k, 1]
+                g[7 * N + 5 + k] = 2.0 * W_SLACK * S[k]
+            if want_jac:
+                for k in range(N):
+                    out["jac"][c, k] = hs_defect_jac(self.tab, X[k], X[k + 1], U[k], self.dt, self.sign)
+        return out

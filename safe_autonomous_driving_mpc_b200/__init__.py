@@ -8,5 +8,6 @@ __path__.insert(0, _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.absp
 from .tracker import BatchedTracker, TrajectoryLoader, TrackerParams  # noqa: E402,F401
 from .environment import ObstaclesFSM, run_simulation  # noqa: E402,F401
 from .planner import PlannerEvaluator  # noqa: E402,F401
+from . import planner_driver  # noqa: E402,F401
 from .simulation import BatchedSimulation, make_scenario  # noqa: E402,F401
 from . import _lib, sharding  # noqa: E402,F401

@@ -1,0 +1,92 @@
+"""Planner host driver (safe-autonomous-driving-mpc_b200/planner_driver.py).
+CPU tests drive it with the oracle evaluator; the GPU test plugs the CUDA evaluator in and must reproduce both."""
+import numpy as np
+import pytest
+
+from conftest import golden, traj_path
+
+
+def _driver():
+    import importlib
+    return importlib.import_module("safe_autonomous_driving_mpc_b200.planner_driver")
+
+
+def test_chunk_matches_reference_optimize(port_tables):
+    """One chunk of the reference NLP (committed Simpson sign) against the UNMODIFIED reference optimizer
+    (TrajectoryOptimizer.optimize, SLSQP + finite differences; tools/make_golden_planner.py --chunk):
+    same objective to 1e-6 relative, same solution to 1e-3, in a comparable number of SLSQP iterations but ~40
+    batched evaluations instead of 1,857 cost + ~15,000 closure calls per Jacobian."""
+    from oracle import planner_port as Q
+    D = _driver()
+    g = golden("planner_chunk_traj1")
+    N = int(g["N"])
+    ev = Q.OracleEvaluator(port_tables[1], N, simpson_sign=-1, s_total=float(g["s_total"]), v_max=float(g["v_max"]))
+    X, U, S, sol, n_eval = D.optimize_chunk(ev, g["x0"], float(g["s_target"]), False)
+    assert sol.status == 0
+    assert abs(sol.fun - float(g["cost"])) <= 1e-6 * abs(float(g["cost"]))
+    assert np.abs(X - g["X"]).max() <= 1e-3 and np.abs(U - g["U"]).max() <= 1e-3 and np.abs(S - g["S"]).max() <= 1e-3
+    assert n_eval < 100
+    assert np.abs(Q.defects(port_tables[1], sol.x, N, simpson_sign=-1)).max() < 1e-6
+
+
+def test_constraint_jacobians_against_finite_differences(port_tables):
+    from oracle import planner_port as Q
+    D = _driver()
+    N = 6
+    ev = Q.OracleEvaluator(port_tables[1], N, simpson_sign=+1, s_total=300.0, v_max=12.0)
+    prob = D.ChunkProblem(ev, np.array([3.0, 0.0, 0.0, 0.0, 2.0]), 23.0, False)
+    rng = np.random.default_rng(3)
+    z = D.initial_guess(N, prob.x0, 23.0, False) + rng.normal(0, 0.05, 8 * N + 5)
+    for fun, jac in ((prob.eq, prob.eq_jac), (prob.ineq, prob.ineq_jac), (lambda y: np.array([prob.cost(y)]),
+                                                                              lambda y: prob.cost_grad(y)[None])):
+        J = jac(z)
+        Jn = np.zeros_like(J)
+        for j in range(len(z)):
+            e = np.zeros_like(z)
+            e[j] = 1e-6
+            Jn[:, j] = (fun(z + e) - fun(z - e)) / 2e-6
+        assert np.abs(J - Jn).max() <= 2e-6 * max(1.0, np.abs(Jn).max())
+
+
+def test_full_short_route_physical_sign(port_tables):
+    """Receding-horizon loop (trajectory_planning.py:491-554) over the first 70 m of trajectory1's curvature profile
+    with the physical Simpson sign: arrives, stops, passes the reference's own trajectory checks."""
+    from oracle import planner_port as Q
+    D = _driver()
+    tab = port_tables[1]
+    s_total, v_max = 70.0, 8.0
+    X, U, S, log = D.optimize_full_trajectory(lambda N, st: Q.OracleEvaluator(tab, N, simpson_sign=+1, s_total=st, v_max=v_max),
+                                              s_total, v_max)
+    assert len(log) >= 2 and log[-1]["final"] and all(c["status"] == 0 for c in log)
+    v = D.reference_trajectory_verdicts(X, U, S, s_total)
+    assert all(v.values()), v
+    assert len(X) == len(U) + 1 == len(S) + 1
+    assert np.all(np.diff(X[:, 0]) > -1e-2)          # the final approach may creep back by < 1 cm (v >= -0.1 tolerance)
+
+
+@pytest.mark.gpu
+def test_gpu_evaluator_drives_the_same_solution(gpu_trackers, port_tables):
+    """The CUDA evaluator behind the driver: the reference's chunk (objective as above) and the physical short route
+    (same verdicts, same trajectory as the CPU-oracle-driven run to 1e-6)."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from oracle import planner_port as Q
+    D = _driver()
+    L, T = gpu_trackers[1]
+    g = golden("planner_chunk_traj1")
+    N = int(g["N"])
+    ev = M.PlannerEvaluator(T, N=N, simpson_sign=-1, s_total=float(g["s_total"]), v_max=float(g["v_max"]))
+    X, U, S, sol, n_eval = D.optimize_chunk(ev, g["x0"], float(g["s_target"]), False)
+    assert sol.status == 0 and abs(sol.fun - float(g["cost"])) <= 1e-6 * abs(float(g["cost"]))
+    assert np.abs(X - g["X"]).max() <= 1e-3
+    s_total, v_max = 70.0, 8.0
+    Xg, Ug, Sg, logg = D.optimize_full_trajectory(
+        lambda n, st: M.PlannerEvaluator(T, N=n, simpson_sign=+1, s_total=st, v_max=v_max), s_total, v_max)
+    Xc, Uc, Sc, logc = D.optimize_full_trajectory(
+        lambda n, st: Q.OracleEvaluator(port_tables[1], n, simpson_sign=+1, s_total=st, v_max=v_max), s_total, v_max)
+    assert all(D.reference_trajectory_verdicts(Xg, Ug, Sg, s_total).values())
+    # SLSQP stops at ftol = 1e-4 (the reference's setting), so rounding-level differences between the two evaluators move
+    # the accepted iterates a little; the trajectories agree to centimetres and the chunk costs to 1e-3
+    assert Xg.shape == Xc.shape and np.abs(Xg - Xc).max() <= 5e-2 and np.abs(Ug - Uc).max() <= 5e-2
+    assert len(logg) == len(logc)
+    for a, b in zip(logg, logc):
+        assert a["N"] == b["N"] and abs(a["cost"] - b["cost"]) <= 1e-3 * max(1.0, abs(b["cost"]))

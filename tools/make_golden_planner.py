@@ -90,5 +90,27 @@ def main():
         print(i, "windows", len(zs), "max |defect| (committed sign)", float(np.abs(np.array(defs)).max()))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--chunk" not in sys.argv:
     main()
+
+
+def make_chunk_solution():
+    """One chunk solved by the UNMODIFIED reference ``TrajectoryOptimizer.optimize`` (SLSQP + finite differences,
+    :351-390) with the synthetic route functions: the known answer for the planner driver."""
+    import time
+    L = TrajectoryLoader(os.path.join(REF, "trajectories", "trajectory1.json"))
+    v_max = float(L.X_ref[:, 4].max())
+    s_total = float(L.X_ref[-1, 0])
+    opt = tp.TrajectoryOptimizer(horizon=N * DT, N=N, dt=DT)
+    x0 = np.array([0.0, 0.0, 0.0, 0.0, 0.0])
+    t0 = time.time()
+    X, U, S = opt.optimize(x0, 20.0, s_total, lambda s: float(L.interp_k(s)), lambda s: 0, lambda s: v_max, False)
+    z = opt.pack(X, U, S)
+    np.savez_compressed(os.path.join(OUT, "planner_chunk_traj1.npz"), X=X, U=U, S=S, cost=float(opt.cost(z, x0, s_total)),
+                        x0=x0, s_target=20.0, s_total=s_total, v_max=v_max, N=N, dt=DT, seconds=time.time() - t0,
+                        versions=np.array([np.__version__, scipy.__version__]))
+    print("chunk: cost", float(opt.cost(z, x0, s_total)), "s_N", X[-1, 0], "seconds", time.time() - t0)
+
+
+if __name__ == "__main__" and "--chunk" in sys.argv:
+    make_chunk_solution()
