@@ -8,7 +8,7 @@ collocation intervals (``PlannerEvaluator.evaluate_host``) instead of ~15,000 Py
 Jacobian.
 
 ``evaluator`` is anything with ``N`` and ``evaluate_host(z, s0=..., want_jac=True) -> dict(defect, jac, node_rows,
-ctrl_rows, cost, cost_grad)``; the tests plug the CPU oracle in here to check the driver logic without a GPU.
+ctrl_rows, cost, cost_grad)``; the tests plug a CPU stand-in in here to check the driver logic without a GPU.
 """
 import numpy as np
 from scipy.optimize import minimize
