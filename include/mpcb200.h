@@ -90,8 +90,14 @@ int mpcb_table_destroy(mpcb_table_handle t);
  * as run_simulation's plant step (trajectory_tracking.py:404). */
 int mpcb_table_get_state(mpcb_table_handle t, double s, double out5[5]);
 int mpcb_table_get_control(mpcb_table_handle t, double s, double out2[2]);
+/* Binary cache of a table (the wire format feeding every config, instead of re-parsing JSON per process): the inputs of
+ * mpcb_table_create behind a 16-byte header; loading re-applies the repair rules of mpcb_table_create. */
+int mpcb_table_save(mpcb_table_handle t, const char* path);
+int mpcb_table_load(mpcb_table_handle* out, const char* path);
 double mpcb_table_s_max(mpcb_table_handle t);
 int mpcb_table_knots(mpcb_table_handle t);
+int mpcb_table_control_knots(mpcb_table_handle t);                       /* KU as given */
+int mpcb_table_raw(mpcb_table_handle t, double* ref_X, double* ref_U);   /* copies the inputs back out ([K][5], [KU][2]) */
 
 /* Solver context on CUDA device `device`: uploads the table, derives the constants.
  * Replaces TrajectoryTracker.__init__ (trajectory_tracking.py:12-47).  The table may be destroyed afterwards. */

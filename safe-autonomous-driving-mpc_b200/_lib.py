@@ -65,6 +65,10 @@ SYMBOLS = {
     "mpcb_default_params": (C.c_int, [C.POINTER(Params)]),
     "mpcb_table_create": (C.c_int, [C.POINTER(C.c_void_p), c_double_p, C.c_int, c_double_p, C.c_int]),
     "mpcb_table_destroy": (C.c_int, [C.c_void_p]),
+    "mpcb_table_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "mpcb_table_load": (C.c_int, [C.POINTER(C.c_void_p), C.c_char_p]),
+    "mpcb_table_raw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpcb_table_control_knots": (C.c_int, [C.c_void_p]),
     "mpcb_table_get_state": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
     "mpcb_table_get_control": (C.c_int, [C.c_void_p, C.c_double, c_double_p]),
     "mpcb_table_s_max": (C.c_double, [C.c_void_p]),

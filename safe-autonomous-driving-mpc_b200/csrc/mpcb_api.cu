@@ -318,6 +318,8 @@ struct mpcb_table {
   int K, Ku;
   double s_max;
   double last_row[5];            // raw X_ref[-1]
+  std::vector<double> raw_X, raw_U;   // inputs as given (for the binary cache)
+  int KU_raw;
 };
 extern "C" {
 
@@ -335,6 +337,9 @@ int mpcb_table_create(mpcb_table_handle* out, const double* ref_X, int K, const 
     for (int k = 0; k < 4; ++k) t->y[(size_t)i * 4 + k] = ref_X[(size_t)i * 5 + 1 + k];
   }
   for (int i = 0; i < t->Ku * 2; ++i) t->u[i] = ref_U[i];
+  t->raw_X.assign(ref_X, ref_X + (size_t)K * 5);
+  t->raw_U.assign(ref_U, ref_U + (size_t)KU * 2);
+  t->KU_raw = KU;
   t->s_max = t->s[K - 1];                                        // :84
   for (int k = 0; k < 5; ++k) t->last_row[k] = ref_X[(size_t)(K - 1) * 5 + k];
   *out = t;
@@ -369,8 +374,50 @@ int mpcb_table_get_control(mpcb_table_handle t, double s, double out2[2]) {
   return MPCB_OK;
 }
 
+// ---- binary cache of the packed table: header {magic, version, K, Ku}, then the raw X rows [K][5]
+// and U rows [Ku][2] as given to mpcb_table_create (the repair and the control-knot rule are re-applied on load, so a
+// cache cannot disagree with the builder) -------------------------------------------------------------------------
+static const unsigned MPCB_TABLE_MAGIC = 0x4d504354u;   // "MPCT"
+
+int mpcb_table_save(mpcb_table_handle t, const char* path) {
+  if (!t || !path) return MPCB_ERR_INVALID;
+  FILE* f = fopen(path, "wb");
+  if (!f) return MPCB_ERR_INVALID;
+  const unsigned hdr[4] = {MPCB_TABLE_MAGIC, 1u, (unsigned)t->K, (unsigned)t->KU_raw};
+  bool ok = fwrite(hdr, sizeof(hdr), 1, f) == 1;
+  ok = ok && fwrite(t->raw_X.data(), sizeof(double), t->raw_X.size(), f) == t->raw_X.size();
+  ok = ok && fwrite(t->raw_U.data(), sizeof(double), t->raw_U.size(), f) == t->raw_U.size();
+  ok = (fclose(f) == 0) && ok;
+  return ok ? MPCB_OK : MPCB_ERR_INVALID;
+}
+
+int mpcb_table_load(mpcb_table_handle* out, const char* path) {
+  if (!out || !path) return MPCB_ERR_INVALID;
+  *out = nullptr;
+  FILE* f = fopen(path, "rb");
+  if (!f) return MPCB_ERR_INVALID;
+  unsigned hdr[4];
+  int rc = MPCB_ERR_INVALID;
+  if (fread(hdr, sizeof(hdr), 1, f) == 1 && hdr[0] == MPCB_TABLE_MAGIC && hdr[1] == 1u && hdr[2] >= 2 && hdr[3] >= 2 &&
+      hdr[2] < (1u << 24) && hdr[3] < (1u << 24)) {
+    std::vector<double> X((size_t)hdr[2] * 5), U((size_t)hdr[3] * 2);
+    if (fread(X.data(), sizeof(double), X.size(), f) == X.size() && fread(U.data(), sizeof(double), U.size(), f) == U.size() &&
+        fgetc(f) == EOF)
+      rc = mpcb_table_create(out, X.data(), (int)hdr[2], U.data(), (int)hdr[3]);
+  }
+  fclose(f);
+  return rc;
+}
+
 double mpcb_table_s_max(mpcb_table_handle t) { return t ? t->s_max : nan(""); }
 int mpcb_table_knots(mpcb_table_handle t) { return t ? t->K : MPCB_ERR_INVALID; }
+int mpcb_table_control_knots(mpcb_table_handle t) { return t ? t->KU_raw : MPCB_ERR_INVALID; }
+int mpcb_table_raw(mpcb_table_handle t, double* ref_X, double* ref_U) {
+  if (!t) return MPCB_ERR_INVALID;
+  if (ref_X) memcpy(ref_X, t->raw_X.data(), t->raw_X.size() * sizeof(double));
+  if (ref_U) memcpy(ref_U, t->raw_U.data(), t->raw_U.size() * sizeof(double));
+  return MPCB_OK;
+}
 
 int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int device) {
   if (!out || !p || !t) return MPCB_ERR_INVALID;

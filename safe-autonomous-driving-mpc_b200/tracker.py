@@ -26,6 +26,17 @@ class TrajectoryLoader:
     keys, or arrays."""
 
     def __init__(self, source, U=None):
+        if isinstance(source, str) and source.endswith(".mpct"):      # binary cache written by save_binary
+            lib = _lib.load()
+            h = C.c_void_p()
+            check(lib.mpcb_table_load(C.byref(h), source.encode()), "mpcb_table_load")
+            K, KU = lib.mpcb_table_knots(h), lib.mpcb_table_control_knots(h)
+            self.X_ref = np.empty((K, 5))
+            self.U_ref = np.empty((KU, 2))
+            check(lib.mpcb_table_raw(h, _dp(self.X_ref), _dp(self.U_ref)))
+            self._h, self._lib = h, lib
+            self.s_max = float(lib.mpcb_table_s_max(h))
+            return
         if isinstance(source, str):
             if source.endswith(".npz"):
                 z = np.load(source)
@@ -57,6 +68,10 @@ class TrajectoryLoader:
         if h:
             self._lib.mpcb_table_destroy(h)
             self._h = None
+
+    def save_binary(self, path):
+        """Write the packed table cache (``.mpct``); ``TrajectoryLoader(path)`` reads it back."""
+        check(self._lib.mpcb_table_save(self._h, str(path).encode()), "mpcb_table_save")
 
     def get_state(self, s):
         out = (C.c_double * 5)()

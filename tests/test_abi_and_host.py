@@ -125,3 +125,25 @@ def test_integration_stub_struct_matches_library():
     exec(m.group(0), ns)
     assert C.sizeof(ns["Params"]) == _lib.load().mpcb_sizeof_params()
     assert [f[0] for f in ns["Params"]._fields_] == [f[0] for f in _lib.Params._fields_]
+
+
+def test_table_binary_cache_roundtrip(tmp_path):
+    """JSON/npz -> table -> .mpct -> table: bit-identical inputs and lookups; a damaged file is rejected."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from safe_autonomous_driving_mpc_b200 import _lib
+    L = M.TrajectoryLoader(traj_path(2))
+    p = str(tmp_path / "t2.mpct")
+    L.save_binary(p)
+    L2 = M.TrajectoryLoader(p)
+    assert np.array_equal(L2.X_ref, L.X_ref) and np.array_equal(L2.U_ref, L.U_ref) and L2.s_max == L.s_max
+    for s in (-3.0, 0.0, 17.3, 640.123, L.s_max - 1e-9, L.s_max, L.s_max + 5):
+        assert np.array_equal(L2.get_state(s), L.get_state(s)) and np.array_equal(L2.get_control(s), L.get_control(s))
+    raw = bytearray(open(p, "rb").read())
+    raw[0] ^= 0xFF
+    bad = str(tmp_path / "bad.mpct")
+    open(bad, "wb").write(raw)
+    with pytest.raises(_lib.MpcbError):
+        M.TrajectoryLoader(bad)
+    open(bad, "wb").write(open(p, "rb").read()[:-8])          # truncated
+    with pytest.raises(_lib.MpcbError):
+        M.TrajectoryLoader(bad)
