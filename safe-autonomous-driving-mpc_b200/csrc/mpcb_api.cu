@@ -749,6 +749,19 @@ int mpcb_last_pass_ms(mpcb_handle h, float* first_ms, float* second_ms, int* n_s
   return MPCB_OK;
 }
 
+#ifdef MPCB_COOP_PROFILE
+int mpcb_debug_coop_profile(unsigned long long* sum8, unsigned long long* max8, int reset) {
+  if (sum8) CK(cudaMemcpyFromSymbol(sum8, g_coop_sum, 64));
+  if (max8) CK(cudaMemcpyFromSymbol(max8, g_coop_max, 64));
+  if (reset) {
+    unsigned long long z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    CK(cudaMemcpyToSymbol(g_coop_sum, z, 64));
+    CK(cudaMemcpyToSymbol(g_coop_max, z, 64));
+  }
+  return MPCB_OK;
+}
+#endif
+
 unsigned long long mpcb_launch_count(mpcb_handle h) { return h ? h->launches : 0ull; }
 
 int mpcb_measure_fp64_peak(mpcb_handle h, double* tflops, float* ms_out) {

@@ -16,6 +16,17 @@
 
 namespace mpcb {
 
+#ifdef MPCB_COOP_PROFILE
+// development: cycles per phase, summed over warps, and the phase split of the slowest warp
+__device__ unsigned long long g_coop_sum[8];
+__device__ unsigned long long g_coop_max[8];
+#define CPROF_T(var) const long long var = clock64()
+#define CPROF_ADD(slot, t0, t1) prof[slot] += (t1) - (t0)
+#else
+#define CPROF_T(var)
+#define CPROF_ADD(slot, t0, t1)
+#endif
+
 constexpr int CW_K = 2;                 // rows per lane
 constexpr int CW_ROWS = 32 * CW_K;      // padded row count (rows >= M_ROWS are null)
 
@@ -31,6 +42,32 @@ struct WarpShared {
   double scal[4];                       // lane-0 scalars broadcast through shared memory
   int iflag[2];
 };
+
+// Cholesky factor held in registers by every lane (the 10x10 factorisation is cheaper done redundantly by all lanes
+// than passed around: no barrier, no shared-memory round trip per column)
+struct RegFactor {
+  double L[NTRI];
+  double rdiag[NV];
+};
+
+__device__ __forceinline__ void chol_regs(RegFactor& F) {
+#pragma unroll
+  for (int j = 0; j < NV; ++j) {
+    double d = F.L[tri(j, j)];
+#pragma unroll
+    for (int k = 0; k < j; ++k) d = fma(-F.L[tri(j, k)], F.L[tri(j, k)], d);
+    const double rs = rsqrt(d);
+    F.L[tri(j, j)] = d * rs;
+    F.rdiag[j] = rs;
+#pragma unroll
+    for (int i = j + 1; i < NV; ++i) {
+      double t = F.L[tri(i, j)];
+#pragma unroll
+      for (int k = 0; k < j; ++k) t = fma(-F.L[tri(i, k)], F.L[tri(j, k)], t);
+      F.L[tri(i, j)] = t * rs;
+    }
+  }
+}
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -90,8 +127,14 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
   Problem& pb = ws.pb;
   const Policy& pl = P.pol[FIRST_PASS ? 1 : 0];
   SolveOut out{MPCB_MAXITER, 0, 0, false};
+#ifdef MPCB_COOP_PROFILE
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 prologue, 1 linearise, 2 rows, 3 factor, 4 iterations, 5 round end
+#endif
+  CPROF_T(tp0);
   if (lane == 0) ws.iflag[0] = prologue(T, P, pb, st) ? 1 : 0;
   __syncwarp();
+  CPROF_T(tp1);
+  CPROF_ADD(0, tp0, tp1);
   const bool screened = ws.iflag[0] != 0;
   bool infeasible = screened;
   out.const_infeasible = screened;
@@ -104,10 +147,10 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
   double a[CW_K][NV], v[CW_K], rho[CW_K], lo[CW_K], hi[CW_K], inrm[CW_K];
   int e[CW_K];
   bool ex[CW_K], aprev[CW_K];
-  double x[NV];       // replicated iterate
-  double kinv[NV];    // row `lane` of K^-1 (lanes 0..9)
+  double x[NV];       // replicated iterate (refreshed at the end of every segment)
+  double g[CW_K][NV]; // K^-1 a_r for this lane's rows: (A x)_r = g_r . (A'w - q)
 #pragma unroll
-  for (int i = 0; i < NV; ++i) { x[i] = 0.0; kinv[i] = 0.0; }
+  for (int i = 0; i < NV; ++i) x[i] = 0.0;
 #pragma unroll
   for (int k = 0; k < CW_K; ++k) { v[k] = 0.0; rho[k] = 0.0; e[k] = 0; aprev[k] = false; }
 
@@ -128,10 +171,16 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
     const int l0 = g * 11, l1 = (g == 2) ? 32 : l0 + 11;
     double s0 = 0.0, s1 = 0.0;
     if (g < 3) {
-      for (int l = l0; l < l1; ++l) {
+      double s0b = 0.0, s1b = 0.0;                 // two accumulators each: half the dependent-add chain
+      int l = l0;
+      for (; l + 1 < l1; l += 2) {
         s0 += ws.red[l][i];
-        if (two) s1 += ws.red[l][NV + i];
+        s0b += ws.red[l + 1][i];
+        if (two) { s1 += ws.red[l][NV + i]; s1b += ws.red[l + 1][NV + i]; }
       }
+      if (l < l1) { s0 += ws.red[l][i]; if (two) s1 += ws.red[l][NV + i]; }
+      s0 += s0b;
+      s1 += s1b;
     }
     o0 = s0 + __shfl_down_sync(FULL, s0, 10) + __shfl_down_sync(FULL, s0, 20);
     o1 = two ? s1 + __shfl_down_sync(FULL, s1, 10) + __shfl_down_sync(FULL, s1, 20) : 0.0;
@@ -139,12 +188,15 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
   };
 
   for (int round = 0; round < max_rounds && !done; ++round) {
+    CPROF_T(tl0);
     if (lane == 0) {
       double cviol;
       linearise(T, P, pb, st, cviol);
       ws.scal[0] = cviol;
     }
     __syncwarp();
+    CPROF_T(tl1);
+    CPROF_ADD(1, tl0, tl1);
     if (ws.scal[0] > P.feas_tol) { infeasible = true; out.const_infeasible = true; }
     out.rounds++;
     // dense rows of this round
@@ -170,12 +222,15 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
       }
       first = false;
     }
+    CPROF_T(tr1);
+    CPROF_ADD(2, tl1, tr1);
     const double loosen = (FIRST_PASS || P.qp_forcing <= 0.0) ? 1.0
                           : dmax(1.0, (step_prev * P.qp_forcing < P.qp_eps_loose ? step_prev * P.qp_forcing : P.qp_eps_loose) / P.eps_p);
     const double eps_p = P.eps_p * loosen, eps_d = P.eps_d * loosen;
     bool conv = false, cert = false;
     for (int seg = 0; seg < pl.max_segments && !conv; ++seg) {
       // ---- factor: K = H + A' diag(rho) A, Cholesky, K^-1 rows ------------------------------------------------
+      CPROF_T(tf0);
 #pragma unroll
       for (int k = 0; k < CW_K; ++k) {
         rho[k] = ex[k] ? pl.lad[e[k]] * inrm[k] : 0.0;
@@ -186,42 +241,36 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
         int i = 0;
         while ((i + 1) * (i + 2) / 2 <= idx) ++i;
         const int j = idx - i * (i + 1) / 2;
-        double acc = st.H[idx];
-        for (int r = 0; r < M_ROWS; ++r) acc = fma(ws.rho[r] * ws.A[r][i], ws.A[r][j], acc);
+        double acc = st.H[idx], acc2 = 0.0;
+        const int r_end = ROW_OBS + N_OBSROW * pb.n_obs;          // rows of absent obstacles carry rho = 0
+        int r = 0;
+        for (; r + 1 < r_end; r += 2) {
+          acc = fma(ws.rho[r] * ws.A[r][i], ws.A[r][j], acc);
+          acc2 = fma(ws.rho[r + 1] * ws.A[r + 1][i], ws.A[r + 1][j], acc2);
+        }
+        if (r < r_end) acc = fma(ws.rho[r] * ws.A[r][i], ws.A[r][j], acc);
+        acc += acc2;
         ws.K[i][j] = acc;
         ws.K[j][i] = acc;
       }
       __syncwarp();
-      for (int j = 0; j < NV; ++j) {             // right-looking Cholesky, lane i owns row i
-        const double rs = rsqrt(ws.K[j][j]);
-        __syncwarp();
-        if (lane == j) { ws.K[j][j] = ws.K[j][j] * rs; ws.rdiag[j] = rs; }
-        if (lane > j && lane < NV) ws.K[lane][j] *= rs;
-        __syncwarp();
-        if (lane > j && lane < NV) {
-          const double lij = ws.K[lane][j];
-          for (int k2 = j + 1; k2 <= lane; ++k2) ws.K[lane][k2] = fma(-lij, ws.K[k2][j], ws.K[lane][k2]);
-        }
-        __syncwarp();
+      RegFactor F;
+#pragma unroll
+      for (int i = 0; i < NV; ++i)
+#pragma unroll
+        for (int j = 0; j <= i; ++j) F.L[tri(i, j)] = ws.K[i][j];
+      chol_regs(F);
+#pragma unroll
+      for (int k = 0; k < CW_K; ++k) {
+        double t[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) t[i] = a[k][i];
+        chol_solve(F, t, g[k]);
       }
-      if (lane < NV) {                           // column `lane` of K^-1: L L' y = e_lane
-        double y[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) y[i] = (i == lane) ? 1.0 : 0.0;
-#pragma unroll
-        for (int j = 0; j < NV; ++j) {
-          y[j] *= ws.rdiag[j];
-#pragma unroll
-          for (int i = j + 1; i < NV; ++i) y[i] = fma(-ws.K[i][j], y[j], y[i]);
-        }
-#pragma unroll
-        for (int j = NV - 1; j >= 0; --j) {
-          kinv[j] = y[j] * ws.rdiag[j];
-#pragma unroll
-          for (int i = 0; i < j; ++i) y[i] = fma(-ws.K[j][i], kinv[j], y[i]);
-        }
-      }
+      double zt0_last = 0.0;
       // ---- iterations ---------------------------------------------------------------------------------------------
+      CPROF_T(tf1);
+      CPROF_ADD(3, tf0, tf1);
       SegStats s{0, 0, 0, 0, 0, 0};
       for (int it = 0; it < pl.segment_iters; ++it) {
         const bool check = (it == pl.segment_iters - 1);
@@ -235,23 +284,18 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
         at_reduce(w, w, false, r0, r1);
         if (lane < NV) ws.vec[0][lane] = r0 - st.q[lane];
         __syncwarp();
-        if (lane < NV) {
-          double xi = 0.0;
+        double rhs[NV];
 #pragma unroll
-          for (int j = 0; j < NV; ++j) xi = fma(kinv[j], ws.vec[0][j], xi);
-          ws.vec[1][lane] = xi;
-        }
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < NV; ++i) x[i] = ws.vec[1][i];
+        for (int i = 0; i < NV; ++i) rhs[i] = ws.vec[0][i];
         double zt[CW_K];
 #pragma unroll
         for (int k = 0; k < CW_K; ++k) {
-          double acc = 0.0;
+          double acc = 0.0, accb = 0.0;
 #pragma unroll
-          for (int i = 0; i < NV; ++i) acc = fma(a[k][i], x[i], acc);
-          zt[k] = acc;
+          for (int i = 0; i < NV; i += 2) { acc = fma(g[k][i], rhs[i], acc); accb = fma(g[k][i + 1], rhs[i + 1], accb); }
+          zt[k] = acc + accb;
         }
+        zt0_last = zt[0];
         if (!check) {
 #pragma unroll
           for (int k = 0; k < CW_K; ++k) v[k] = fma(pl.relax, zt[k] - z[k], v[k]);
@@ -294,7 +338,12 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
           s.sup = warp_sum(sup);
         }
       }
+      // lanes 0..9 own the box rows, whose row value is x_i itself
+#pragma unroll
+      for (int i = 0; i < NV; ++i) x[i] = __shfl_sync(FULL, zt0_last, i);
       out.iters += pl.segment_iters;
+      CPROF_T(ti1);
+      CPROF_ADD(4, tf1, ti1);
       if (s.rp <= eps_p && s.rd <= eps_d) conv = true;
       else if (!FIRST_PASS && s.nd > 1e-9 && s.atdy <= P.eps_inf * s.nd && s.sup < -P.eps_inf * s.nd &&
                s.bad <= P.eps_inf * s.nd) { conv = true; cert = true; }
@@ -314,6 +363,18 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
   // an infeasibility verdict is final only on a point the pass actually converged to (or, in the robust pass, gave
   // up on): a first pass that could not close its QP hands the problem over whatever the screens said
   if (infeasible && (!FIRST_PASS || out.status == 0)) out.status = 2;
+#ifdef MPCB_COOP_PROFILE
+  if (lane == 0) {
+    long long tot = 0;
+    for (int i = 0; i < 6; ++i) { tot += prof[i]; atomicAdd(&g_coop_sum[i], (unsigned long long)prof[i]); }
+    atomicAdd(&g_coop_sum[6], (unsigned long long)tot);
+    atomicAdd(&g_coop_sum[7], 1ull);
+    if ((unsigned long long)tot > atomicMax(&g_coop_max[6], (unsigned long long)tot)) {   // racy snapshot: development aid only
+      for (int i = 0; i < 6; ++i) g_coop_max[i] = (unsigned long long)prof[i];
+      g_coop_max[7] = (unsigned long long)out.iters * 1000ull + (unsigned long long)out.rounds;
+    }
+  }
+#endif
   __syncwarp();
   if (lane < NV) pb.U[lane] = clipd(pb.U[lane], P.umin[lane & 1], P.umax[lane & 1]);
   __syncwarp();
