@@ -29,7 +29,9 @@
 
 // Loop control is uniform over the whole CTA (all threads reach every barrier): the CTA walks through the
 // straight-line solver code together, so one instruction stream per CTA goes through the instruction caches.
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && defined(MPCB_WARP_UNIFORM)
+#define MPCB_ALL(pred) (__all_sync(0xffffffffu, pred) != 0)
+#elif defined(__CUDA_ARCH__)
 #define MPCB_ALL(pred) (__syncthreads_and(pred) != 0)
 #else
 #define MPCB_ALL(pred) (pred)

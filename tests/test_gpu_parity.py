@@ -218,3 +218,56 @@ def test_device_tensor_entry_point(gpu_trackers, port_tables):
     assert np.array_equal(out["status"].cpu().numpy(), host["status"])
     assert np.array_equal(out["obj"].cpu().numpy(), host["obj"])
     assert T.launch_count() > 0 and T.last_kernel_ms() > 0.0
+
+
+def test_execution_shapes_agree(gpu_trackers, port_tables):
+    """The same problems through every execution shape -- two-pass with the warp-per-problem robust pass (default),
+    two-pass with the thread-per-problem robust pass, single robust pass, and the small-batch warp-per-problem path --
+    give the same flags and the same controls to 1e-6 (the shapes differ in summation order only)."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from oracle import tracker_port as P
+    L, T = gpu_trackers[3]
+    x0, obs, n = P.monte_carlo_problems(port_tables[3], 6000)
+    ref = {k: v.copy() for k, v in T.solve_batch_host(x0, obs, n).items()}
+    variants = dict(thread_pass2=dict(coop_pass2=0), robust_only=dict(fast_pass=0), no_small_coop=dict(coop_max_batch=0))
+    for name, kw in variants.items():
+        Tv = M.BatchedTracker(L, **kw)
+        r = Tv.solve_batch_host(x0, obs, n)
+        agree = r["status"] == ref["status"]
+        assert agree.mean() > 0.999, name                     # borderline flags may flip between solver paths
+        ok = agree & (ref["status"] == 0)
+        assert np.abs(r["U"] - ref["U"])[ok].max() <= 1e-6, name
+    small = T.solve_batch_host(x0[:700], obs[:700], n[:700])   # B <= coop_max_batch: warp-per-problem first pass
+    same = small["status"] == ref["status"][:700]
+    assert same.mean() > 0.999
+    ok = same & (small["status"] == 0)
+    assert np.abs(small["U"] - ref["U"][:700])[ok].max() <= 1e-6
+
+
+def test_argument_errors_and_degenerate_sizes(gpu_trackers):
+    import ctypes as C
+    from safe_autonomous_driving_mpc_b200 import _lib
+    L, T = gpu_trackers[1]
+    lib = T._lib
+    assert lib.mpcb_solve_batch_host(T._h, 0, None, None, None, None, None, None, None, None, None, None) == 0   # B = 0
+    assert lib.mpcb_solve_batch_host(T._h, -1, None, None, None, None, None, None, None, None, None, None) == -1
+    assert lib.mpcb_solve_batch_host(T._h, 4, None, None, None, None, None, None, None, None, None, None) == -1  # null inputs
+    assert lib.mpcb_solve_batch_host(None, 1, None, None, None, None, None, None, None, None, None, None) == -1
+    x0 = np.array([[10.0, 0.0, 0.0, 0.0, 5.0]] * 3)
+    obs = np.zeros((3, 2, 2))
+    # n_obs outside 0..2 is clamped like the reference's list slicing would
+    r = T.solve_batch_host(x0, obs, np.array([0, -3, 0], dtype=np.int32))
+    assert np.array_equal(r["U"][0], r["U"][1])
+    # states at and beyond the end of the table (get_state clamps to the last row, trajectory_loader.py:90-91)
+    xe = np.array([[L.s_max - 0.5, 0.0, 0.0, 0.0, 1.0], [L.s_max + 3.0, 0.0, 0.0, 0.0, 1.0]])
+    r = T.solve_batch_host(xe, np.zeros((2, 2, 2)), np.zeros(2, dtype=np.int32))
+    assert np.all(np.isfinite(r["U"])) and np.all(np.isfinite(r["obj"]))
+    p = _lib.Params()
+    lib.mpcb_default_params(C.byref(p))
+    p.N = 7
+    h = C.c_void_p()
+    assert lib.mpcb_create(C.byref(h), C.byref(p), L._h, 0) == -4          # MPCB_ERR_UNSUPPORTED
+    p.N = 5
+    p.alpha = 2.5
+    assert lib.mpcb_create(C.byref(h), C.byref(p), L._h, 0) == -1
+    assert lib.mpcb_create(C.byref(h), C.byref(p), L._h, 99) != 0

@@ -6,14 +6,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
-    "T128_C2_M3": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=3"],      # v rho
-    "T128_C2_M7": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7"],      # v rho hio
-    "T128_C2_M35": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=35"],    # v rho q lane_c
-    "T128_C2_M13": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=13"],    # v hio D O
-    "T128_C2_M18": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=18"],    # rho L
-    "T128_C2_M1": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=1"],      # v
-    "T128_C2_M9": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=9"],      # v D O
-    "T96_C2_M15": ["MPCB_SOLVE_THREADS=96", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=15"],      # v rho hio D O (140)
+    "T128_C2_M7": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7"],
+    "T128_C2_M7_W": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
+    "T64_C4_M7_W": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
+    "T32_C8_M7_W": ["MPCB_SOLVE_THREADS=32", "MPCB_SOLVE_CTAS=8", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
+    "T256_C1_M7_W": ["MPCB_SOLVE_THREADS=256", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
 }
 if sys.argv[1] == "build":
     import importlib
