@@ -162,7 +162,7 @@ def run_reference(args):
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     return 0
 
 
@@ -309,11 +309,20 @@ def run_ours(args):
                            "note": "last timed step on rank 0: two-level first pass over all problems, robust ladder "
                                    "pass over the uncertified leftovers"},
                 "wall_s_timed_region": t_wall}
-        print(json.dumps(line), flush=True)
+        print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def _quiet_stdout():
+    """Libraries (NCCL's version banner, for one) write to fd 1; the contract is ONE JSON line on stdout.  Point fd 1 at
+    stderr for the duration of the run and return a writer on the real stdout for the final line."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return os.fdopen(real, "w")
 
 
 def main():
@@ -325,6 +334,8 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    global _OUT
+    _OUT = _quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
     return run_ours(args)
