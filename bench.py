@@ -284,7 +284,11 @@ def run_ours(args):
         mp_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(mp_file))["hbm_gbs"] if os.path.exists(mp_file) else 6650.0
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None,
+                    "frac": achieved / peak_tf,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the two solve launches of one step, from the
+                    # ncu --set full capture of this command (profiles/r01_v4_solve_kernels_ncu.txt); algorithmic
+                    # bytes are 416 B/solve = 27.3 MB: the excess is thread-local spill traffic
+                    "traffic": 84.3e6 + 0.45e6,
                     "note": "path is bound by the FP64 FMA pipe, not HBM or tensor cores (SURVEY 8d); peak = DFMA "
                             "loop measured in this run (mpcb_measure_fp64_peak); flops per SURVEY 8d formula with "
                             "the kernel's own per-problem round/iteration counts",
