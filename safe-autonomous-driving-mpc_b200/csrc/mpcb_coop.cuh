@@ -37,7 +37,7 @@ struct WarpShared {
   double rho[CW_ROWS];
   double K[NV][NV + 1];                 // K, then its Cholesky factor (lower)
   double rdiag[NV];
-  double red[32][2 * NV + 1];           // per-lane partial sums of the A't reductions (odd stride: conflict free)
+  alignas(16) double tv[2][CW_ROWS];    // row weights published for the A't products
   double vec[2][NV];                    // reduced vector / iterate, broadcast to the lanes
   double scal[4];                       // lane-0 scalars broadcast through shared memory
   int iflag[2];
@@ -78,6 +78,15 @@ __device__ __forceinline__ double warp_max(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
+}
+
+// max over the warp of a non-negative finite double: its bit pattern orders like an unsigned 64-bit integer, so two
+// 32-bit REDUX instructions replace five shuffle / compare steps
+__device__ __forceinline__ double warp_max_nonneg(double v) {
+  const unsigned hi = (unsigned)__double2hiint(v), lo = (unsigned)__double2loint(v);
+  const unsigned mh = __reduce_max_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_max_sync(0xffffffffu, hi == mh ? lo : 0u);
+  return __hiloint2double((int)mh, (int)ml);
 }
 
 // dense coefficients, bounds and 1/|a|^2 of row r at the current linearisation (same rows as for_rows)
@@ -154,31 +163,31 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
 #pragma unroll
   for (int k = 0; k < CW_K; ++k) { v[k] = 0.0; rho[k] = 0.0; e[k] = 0; aprev[k] = false; }
 
-  // o[i] = sum over all rows of a_r[i] t_r for NVEC right-hand sides at once, result on lanes 0..9 (lane i gets
-  // component i).  Partial sums go through shared memory: every lane writes its 10 partials, lanes (i, g) with
-  // i = lane % 10, g = lane / 10 < 3 add up a third of the lanes each, two shuffles combine the thirds.
+  // o[i] = sum over all rows of a_r[i] t_r for one or two row-weight vectors at once, result on lanes 0..9 (lane i
+  // gets component i).  Every lane publishes the weights of its rows; lane (i, part), i = lane % 10, part = lane / 10
+  // < 3, adds up column i of A' over a third of the rows (straight-line, loads issued ahead of the FMAs), two
+  // shuffles combine the thirds.  (Rows 41 and up are null: zero coefficients, zero weights.)
   auto at_reduce = [&](const double (&t0)[CW_K], const double (&t1)[CW_K], bool two, double& o0, double& o1) {
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      double p = 0.0, q2 = 0.0;
-#pragma unroll
-      for (int k = 0; k < CW_K; ++k) { p = fma(a[k][i], t0[k], p); q2 = fma(a[k][i], t1[k], q2); }
-      ws.red[lane][i] = p;
-      if (two) ws.red[lane][NV + i] = q2;
-    }
+    ws.tv[0][lane] = t0[0];
+    ws.tv[0][lane + 32] = t0[1];
+    if (two) { ws.tv[1][lane] = t1[0]; ws.tv[1][lane + 32] = t1[1]; }
     __syncwarp();
-    const int i = lane % NV, g = lane / NV;
-    const int l0 = g * 11, l1 = (g == 2) ? 32 : l0 + 11;
-    double s0 = 0.0, s1 = 0.0;
-    if (g < 3) {
-      double s0b = 0.0, s1b = 0.0;                 // two accumulators each: half the dependent-add chain
-      int l = l0;
-      for (; l + 1 < l1; l += 2) {
-        s0 += ws.red[l][i];
-        s0b += ws.red[l + 1][i];
-        if (two) { s1 += ws.red[l][NV + i]; s1b += ws.red[l + 1][NV + i]; }
+    const int i = lane % NV, part = lane / NV;
+    double s0 = 0.0, s0b = 0.0, s1 = 0.0, s1b = 0.0;
+    if (part < 3) {
+      const int r0 = part * 14;
+#pragma unroll
+      for (int m = 0; m < 14; m += 2) {
+        const double2 ta = *reinterpret_cast<const double2*>(&ws.tv[0][r0 + m]);
+        const double c0 = ws.A[r0 + m][i], c1 = ws.A[r0 + m + 1][i];
+        s0 = fma(c0, ta.x, s0);
+        s0b = fma(c1, ta.y, s0b);
+        if (two) {
+          const double2 tb = *reinterpret_cast<const double2*>(&ws.tv[1][r0 + m]);
+          s1 = fma(c0, tb.x, s1);
+          s1b = fma(c1, tb.y, s1b);
+        }
       }
-      if (l < l1) { s0 += ws.red[l][i]; if (two) s1 += ws.red[l][NV + i]; }
       s0 += s0b;
       s1 += s1b;
     }
@@ -186,6 +195,17 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
     o1 = two ? s1 + __shfl_down_sync(FULL, s1, 10) + __shfl_down_sync(FULL, s1, 20) : 0.0;
     __syncwarp();
   };
+
+  // packed-triangle entries of K this lane accumulates (two passes over the 55 entries)
+  int ki[2], kj[2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) {
+    const int idx = lane + 32 * m;
+    int i = 0;
+    while ((i + 1) * (i + 2) / 2 <= idx) ++i;
+    ki[m] = i;
+    kj[m] = idx - i * (i + 1) / 2;
+  }
 
   for (int round = 0; round < max_rounds && !done; ++round) {
     CPROF_T(tl0);
@@ -237,21 +257,29 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
         ws.rho[lane + 32 * k] = rho[k];
       }
       __syncwarp();
-      for (int idx = lane; idx < NTRI; idx += 32) {
-        int i = 0;
-        while ((i + 1) * (i + 2) / 2 <= idx) ++i;
-        const int j = idx - i * (i + 1) / 2;
-        double acc = st.H[idx], acc2 = 0.0;
-        const int r_end = ROW_OBS + N_OBSROW * pb.n_obs;          // rows of absent obstacles carry rho = 0
-        int r = 0;
-        for (; r + 1 < r_end; r += 2) {
-          acc = fma(ws.rho[r] * ws.A[r][i], ws.A[r][j], acc);
-          acc2 = fma(ws.rho[r + 1] * ws.A[r + 1][i], ws.A[r + 1][j], acc2);
+      // K = H + sum_r rho_r a_r a_r': box rows only touch the diagonal; the other rows in straight-line blocks (lane
+      // rows, speed rows, one block per present obstacle) so that a block's loads are issued ahead of its FMAs
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const int idx = lane + 32 * m;
+        if (idx < NTRI) {
+          const int i = ki[m], j = kj[m];
+          double acc = st.H[idx] + (i == j ? ws.rho[i] : 0.0), acc2 = 0.0;
+          auto kblock = [&](auto r0t, auto r1t) {
+            constexpr int R0 = decltype(r0t)::value, R1 = decltype(r1t)::value;
+#pragma unroll
+            for (int r = R0; r < R1; r += 2) {
+              acc = fma(ws.rho[r] * ws.A[r][i], ws.A[r][j], acc);
+              if (r + 1 < R1) acc2 = fma(ws.rho[r + 1] * ws.A[r + 1][i], ws.A[r + 1][j], acc2);
+            }
+          };
+          kblock(std::integral_constant<int, ROW_LANE>{}, std::integral_constant<int, ROW_OBS>{});
+          if (pb.n_obs >= 1) kblock(std::integral_constant<int, ROW_OBS>{}, std::integral_constant<int, ROW_OBS + N_OBSROW>{});
+          if (pb.n_obs == 2) kblock(std::integral_constant<int, ROW_OBS + N_OBSROW>{}, std::integral_constant<int, M_ROWS>{});
+          acc += acc2;
+          ws.K[i][j] = acc;
+          ws.K[j][i] = acc;
         }
-        if (r < r_end) acc = fma(ws.rho[r] * ws.A[r][i], ws.A[r][j], acc);
-        acc += acc2;
-        ws.K[i][j] = acc;
-        ws.K[j][i] = acc;
       }
       __syncwarp();
       RegFactor F;
@@ -271,7 +299,7 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
       // ---- iterations ---------------------------------------------------------------------------------------------
       CPROF_T(tf1);
       CPROF_ADD(3, tf0, tf1);
-      SegStats s{0, 0, 0, 0, 0, 0};
+      bool qp_ok = false, cert_ok = false;
       for (int it = 0; it < pl.segment_iters; ++it) {
         const bool check = (it == pl.segment_iters - 1);
         double z[CW_K], w[CW_K];
@@ -329,13 +357,15 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
         }
         double o1, o2;
         at_reduce(t1, t2, !FIRST_PASS, o1, o2);
-        s.rp = warp_max(rp);
-        s.rd = warp_max(lane < NV ? fabs(o1) : 0.0);
-        if (!FIRST_PASS) {
-          s.atdy = warp_max(lane < NV ? fabs(o2) : 0.0);
-          s.nd = warp_max(nd);
-          s.bad = warp_max(bad);
-          s.sup = warp_sum(sup);
+        // convergence and certificate tests as warp votes (same decisions as comparing the warp-wide maxima)
+        qp_ok = __all_sync(FULL, rp <= eps_p) && __all_sync(FULL, lane < NV ? fabs(o1) <= eps_d : true);
+        if (!FIRST_PASS && !qp_ok) {
+          const double ndw = warp_max_nonneg(nd);
+          const double thr = P.eps_inf * ndw;
+          const bool c_at = __all_sync(FULL, lane < NV ? fabs(o2) <= thr : true);
+          const bool c_bad = __all_sync(FULL, bad <= thr);
+          const double supw = warp_sum(sup);
+          cert_ok = ndw > 1e-9 && c_at && c_bad && supw < -thr;
         }
       }
       // lanes 0..9 own the box rows, whose row value is x_i itself
@@ -344,9 +374,8 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
       out.iters += pl.segment_iters;
       CPROF_T(ti1);
       CPROF_ADD(4, tf1, ti1);
-      if (s.rp <= eps_p && s.rd <= eps_d) conv = true;
-      else if (!FIRST_PASS && s.nd > 1e-9 && s.atdy <= P.eps_inf * s.nd && s.sup < -P.eps_inf * s.nd &&
-               s.bad <= P.eps_inf * s.nd) { conv = true; cert = true; }
+      if (qp_ok) conv = true;
+      else if (cert_ok) { conv = true; cert = true; }
     }
     double step = 0.0;
 #pragma unroll

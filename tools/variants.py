@@ -6,6 +6,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
+    "ROWSPACE": [],
+    "NOROWSPACE": ["MPCB_COOP_ROWSPACE=0"],
     "T128_C2_M7": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7"],
     "T128_C2_M7_W": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
     "T64_C4_M7_W": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
