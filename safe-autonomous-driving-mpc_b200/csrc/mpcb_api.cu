@@ -31,19 +31,25 @@ constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::SHARED * SOLVE_THREAD
 constexpr int EVAL_THREADS = 128;
 
 // Final evaluation at U* (predict, cost, constraint rows in the reference's order), flags, outputs.  In the first pass a
-// problem that is not certified is appended to the work list of the robust pass instead (its iteration counts are
-// still recorded, the robust pass adds its own).
+// problem that is not certified is appended to the work list of the next pass instead (fb_list == nullptr: the caller
+// goes on itself); its iteration counts are still recorded, the next pass adds its own.  Returns "written out".
 template <bool FIRST_PASS>
-__device__ __forceinline__ void finalize(const DevTable& T, const DevParams& P, const Problem& pb, const SolveOut& so, int b,
+__device__ __forceinline__ bool finalize(const DevTable& T, const DevParams& P, const Problem& pb, const SolveOut& so, int b,
                                          bool accumulate, double* __restrict__ U_out, double* __restrict__ Xpred_out,
                                          double* __restrict__ obj_out, int* __restrict__ status_out,
                                          int* __restrict__ iters_out, double* __restrict__ cmin_out,
                                          unsigned long long* __restrict__ active_out, int* __restrict__ fb_list,
                                          int* __restrict__ fb_count) {
-  if (FIRST_PASS && so.status == MPCB_MAXITER) {                   // not certified: leave it to the robust pass
-    fb_list[atomicAdd(fb_count, 1)] = b;
-    if (iters_out) { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
-    return;
+  auto defer = [&]() {
+    if (fb_list) fb_list[atomicAdd(fb_count, 1)] = b;
+    if (iters_out) {
+      if (accumulate) { iters_out[2 * b] += so.rounds; iters_out[2 * b + 1] += so.iters; }
+      else { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
+    }
+  };
+  if (FIRST_PASS && so.status == MPCB_MAXITER) {                   // not certified: leave it to the next pass
+    defer();
+    return false;
   }
 
   // final evaluation at U*: predict, cost, constraint rows in the reference's order
@@ -69,9 +75,8 @@ __device__ __forceinline__ void finalize(const DevTable& T, const DevParams& P, 
   int status = so.status;
   if (cmin < -P.feas_tol) {
     if (FIRST_PASS && !so.const_infeasible) {                      // a violated row the first pass cannot explain
-      fb_list[atomicAdd(fb_count, 1)] = b;
-      if (iters_out) { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
-      return;
+      defer();
+      return false;
     }
     status = MPCB_INFEASIBLE;
   }
@@ -92,6 +97,7 @@ __device__ __forceinline__ void finalize(const DevTable& T, const DevParams& P, 
   }
   if (cmin_out) cmin_out[b] = cmin;
   if (active_out) active_out[b] = act;
+  return true;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -137,24 +143,35 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
 
 // ------------------------------------------------------------------------------------------------
 // Warp-per-problem kernel (mpcb_coop.cuh): the robust pass over the work list, and whole small batches.
+// Persistent warps: the grid is what is resident at once (COOP_CTAS per SM) and every warp pulls its next problem
+// from a device counter, so a long problem occupies one warp and never a CTA slot other problems are waiting for.
 // ------------------------------------------------------------------------------------------------
 constexpr int COOP_WARPS = 4;
+#ifndef MPCB_COOP_CTAS
+#define MPCB_COOP_CTAS 2
+#endif
+constexpr int COOP_CTAS = MPCB_COOP_CTAS;   // CTAs per SM the kernel is compiled for
+constexpr int FB_HDR = 4;               // work-list header: count, cursor of the first pass, cursor of the second, pad
 constexpr size_t COOP_SMEM = sizeof(WarpShared) * COOP_WARPS;
 
 template <bool FIRST_PASS>
-__global__ void __launch_bounds__(COOP_WARPS * 32)
+__global__ void __launch_bounds__(COOP_WARPS * 32, COOP_CTAS)
 mpcb_coop_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
                  const int* __restrict__ idx, const int* __restrict__ n_idx,
                  const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
                  double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
                  int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
-                 unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+                 unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count,
+                 int* __restrict__ cursor) {
   extern __shared__ double coop_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpShared& ws = reinterpret_cast<WarpShared*>(coop_smem)[wid];
   const int n_work = idx ? min(*n_idx, B) : B;
-  const int n_warps = gridDim.x * COOP_WARPS;
-  for (int t = blockIdx.x * COOP_WARPS + wid; t < n_work; t += n_warps) {
+  for (;;) {
+    int t = 0;
+    if (lane == 0) t = atomicAdd(cursor, 1);
+    t = __shfl_sync(0xffffffffu, t, 0);
+    if (t >= n_work) break;
     const int b = idx ? idx[t] : t;
     __syncwarp();
     if (lane < 5) ws.pb.x0[lane] = x0[(size_t)b * 5 + lane];
@@ -288,7 +305,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 extern "C" {
 
-int mpcb_abi_version(void) { return 3; }
+int mpcb_abi_version(void) { return 4; }
 unsigned long long mpcb_sizeof_params(void) { return sizeof(mpcb_params); }
 unsigned long long mpcb_sizeof_planner_params(void) { return sizeof(mpcb_planner_params); }
 
@@ -498,14 +515,14 @@ int mpcb_destroy(mpcb_handle h) {
 // fallback-list storage for a batch of B problems split into up to HOST_CHUNKS independently launched parts
 static const int HOST_CHUNKS = 4;
 static int ensure_fb(mpcb_handle h, int B) {
-  if (!h->params.fast_pass || B + HOST_CHUNKS <= h->fb_cap) return MPCB_OK;
+  if (!h->params.fast_pass || B + FB_HDR * HOST_CHUNKS <= h->fb_cap) return MPCB_OK;
   if (h->fb) { CK(cudaFree(h->fb)); h->fb = nullptr; h->fb_cap = 0; }
-  if (cudaMalloc(&h->fb, sizeof(int) * ((size_t)B + HOST_CHUNKS)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
-  h->fb_cap = B + HOST_CHUNKS;
+  if (cudaMalloc(&h->fb, sizeof(int) * ((size_t)B + FB_HDR * HOST_CHUNKS)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
+  h->fb_cap = B + FB_HDR * HOST_CHUNKS;
   return MPCB_OK;
 }
 
-// Enqueue the solve of B problems on `st`.  fb = [count, idx[B]] (device ints) for the two-pass scheme.
+// Enqueue the solve of B problems on `st`.  fb = [count, cursor, cursor, pad, idx[B]] (device ints) for the two-pass scheme.
 // timed: bracket the passes with the handle's events (single-stream callers only).
 static int launch_solve(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs, double* U_out,
                         double* Xpred_out, double* obj_out, int* status_out, int* iters_out, double* cmin_out,
@@ -518,14 +535,14 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
   if (timed) CK(cudaEventRecord(h->ev0, st));
   if (h->params.fast_pass) {
     int* fb_count = fb;
-    int* fb_list = fb + 1;
-    CK(cudaMemsetAsync(fb_count, 0, sizeof(int), st));
+    int* fb_list = fb + FB_HDR;
+    CK(cudaMemsetAsync(fb, 0, sizeof(int) * FB_HDR, st));
     if (whole_call && B <= h->params.coop_max_batch) {   // (parts of a larger call keep the shape of the whole call)
       // small batch: too few problems to fill the GPU with one thread each -> one warp per problem, for latency
-      const int g1 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * 4);
+      const int g1 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * COOP_CTAS);
       mpcb_coop_kernel<true><<<g1, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs, U_out,
                                                             Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
-                                                            fb_list, fb_count);
+                                                            fb_list, fb_count, fb + 1);
     } else {
       mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
                                                                       U_out, Xpred_out, obj_out, status_out, iters_out,
@@ -536,10 +553,10 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
     // second pass over whatever the first did not certify
     if (h->params.coop_pass2) {
       // one warp per problem: the leftovers are few and hard, what matters is their latency
-      const int g2 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * 4);
+      const int g2 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * COOP_CTAS);
       mpcb_coop_kernel<false><<<g2, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs, U_out,
                                                              Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
-                                                             nullptr, nullptr);
+                                                             nullptr, nullptr, fb + 2);
     } else {
       // thread per problem; CTAs beyond the list length exit at once (one warp per CTA when the working set is
       // thread-local: the few leftover warps then never wait for each other)
@@ -658,7 +675,7 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
     rc = launch_solve(h, (int)n, (double*)(w + o_x0) + lo * 5, (double*)(w + o_obs) + lo * 4, (int*)(w + o_n) + lo,
                       dU + lo * 10, dX ? dX + lo * 30 : nullptr, dobj ? dobj + lo : nullptr, dst ? dst + lo : nullptr,
                       dit ? dit + lo * 2 : nullptr, dcm ? dcm + lo : nullptr, dac ? dac + lo : nullptr, st,
-                      h->fb + lo + c, false, false);
+                      h->fb + lo + FB_HDR * c, false, false);
     if (rc != MPCB_OK) return rc;
     CK(cudaMemcpyAsync(U_out + lo * 10, dU + lo * 10, n * 80, cudaMemcpyDeviceToHost, st));
     if (Xpred_out) CK(cudaMemcpyAsync(Xpred_out + lo * 30, dX + lo * 30, n * 240, cudaMemcpyDeviceToHost, st));

@@ -39,6 +39,10 @@ struct WarpShared {
   double rdiag[NV];
   alignas(16) double tv[2][CW_ROWS];    // row weights published for the A't products
   double vec[2][NV];                    // reduced vector / iterate, broadcast to the lanes
+  double jv[2][3][NV];                  // linearisation: residual Jacobian rows of a step (d, o, v), double buffered
+  double xh[NH + 1][2];                 // linearisation: (d_j, o_j) of the nominal rollout
+  double lk[NH + 1][8];                 // linearisation: reference values and slopes at s_0 .. s_5
+  double ur[NH][2];                     // warm start: reference controls at the five probe positions
   double scal[4];                       // lane-0 scalars broadcast through shared memory
   int iflag[2];
 };
@@ -129,6 +133,143 @@ __device__ __forceinline__ void coop_row(const DevParams& P, const Store<1, 0u>&
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Linearisation by the whole warp: same arithmetic as linearise() of mpcb_solver.cuh, entry by entry in the same
+// order, spread over the lanes.  The nominal rollout and the table lookups run redundantly on every lane (same
+// instruction stream, broadcast loads); lane c < 10 carries column c of the sensitivities d(d_j)/dU, d(o_j)/dU and
+// component c of the gradient; the 55 entries of H belong to the lanes like the entries of K (ki, kj); the residual
+// Jacobian rows of a step reach their consumers through shared memory.  Fills st.H, q, D, O, lane_c, lane_inrm.
+// ------------------------------------------------------------------------------------------------
+template <class ST>
+__device__ void coop_linearise(const DevTable& T, const DevParams& P, WarpShared& ws, const ST& st, int lane,
+                               const int (&ki)[2], const int (&kj)[2], double& const_viol) {
+  const double h = P.h;
+  Problem& pb = ws.pb;
+  const int c = lane, ci = lane >> 1;
+  const bool cb = (lane & 1) != 0, col = lane < NV;
+  double Hm[2];
+#pragma unroll
+  for (int m = 0; m < 2; ++m) Hm[m] = (lane + 32 * m < NTRI && ki[m] == kj[m]) ? 2.0 * P.wu[ki[m] & 1] : 0.0;
+  double g = col ? 2.0 * P.wu[c & 1] * pb.U[c] : 0.0;
+  double X[5] = {pb.x0[0], pb.x0[1], pb.x0[2], pb.x0[3], pb.x0[4]};
+  double dD = 0.0, dO = 0.0;
+  double val[4] = {0.0, 0.0, 0.0, 0.0}, slope[4] = {0.0, 0.0, 0.0, 0.0};
+  double cv = 0.0;
+  // s_j and v_j do not depend on the reference values (s' = v, v' = b): the six table lookups of the rollout are
+  // independent of one another, so lanes 0..5 do one each -- one memory round trip instead of six in a row
+  {
+    double sj = X[0], vj = X[4], s_mine = X[0];
+#pragma unroll
+    for (int j = 0; j <= NH; ++j) {
+      if (lane == j) s_mine = sj;
+      if (j < NH) { sj = sj + h * vj; vj = vj + h * pb.U[2 * j + 1]; }
+    }
+    if (lane <= NH) {
+      int hint = pb.hint[lane];
+      lookup_state_hint(T, s_mine, val, slope, hint);
+      pb.hint[lane] = hint;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) { ws.lk[lane][q] = val[q]; ws.lk[lane][4 + q] = slope[q]; }
+    }
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j <= NH; ++j) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { val[q] = ws.lk[j][q]; slope[q] = ws.lk[j][4 + q]; }
+    if (lane == 0) { ws.xh[j][0] = X[1]; ws.xh[j][1] = X[2]; }
+    if (j >= 1) {
+      // residual rows of step j (accumulate_step<j>): this lane's column of J_d, J_o, J_v
+      const double ds = (ci < j - 1) ? h * h * (double)(j - 1 - ci) : 0.0;
+      double Jd = 0.0, Jo = 0.0, Jv = 0.0;
+      if (col && cb && ci < j) Jv = h - slope[3] * ds;
+      if (col && ci < j - 1) {
+        Jd = cb ? dD - slope[0] * ds : dD;
+        Jo = cb ? dO - slope[1] * ds : dO;
+      }
+      const double rd = X[1] - val[0], ro = X[2] - val[1], rv = X[4] - val[3];
+      if (col && ci < j - 1) g += 2.0 * (P.wd * rd * Jd + P.wo * ro * Jo);
+      if (col && cb && ci < j) g += 2.0 * P.wv * rv * Jv;
+      double (*jv)[NV] = ws.jv[j & 1];
+      if (col) { jv[0][c] = Jd; jv[1][c] = Jo; jv[2][c] = Jv; }
+      // lane rows of step j (lane_rows<j>): sensitivities as they stand before the next advance
+      if (j >= 2 && col && c < 2 * (j - 1)) { st.D[doff(j - 2) + c] = dD; st.O[doff(j - 2) + c] = dO; }
+      __syncwarp();
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        if (lane + 32 * m < NTRI) {
+          const int p = ki[m], q = kj[m];
+          if (j >= 2) {
+            Hm[m] = fma((2.0 * P.wd) * jv[0][p], jv[0][q], Hm[m]);
+            Hm[m] = fma((2.0 * P.wo) * jv[1][p], jv[1][q], Hm[m]);
+          }
+          Hm[m] = fma((2.0 * P.wv) * jv[2][p], jv[2][q], Hm[m]);
+        }
+      }
+      if (j == 1) {
+        cv = dmax(cv, fabs(X[1]) - P.sld);
+        cv = dmax(cv, fabs(X[1] + P.alpha_lane[2] * X[2]) - P.sld);
+      }
+    }
+    if (j < NH) {
+      // advance j -> j + 1
+      const double d = X[1], o = X[2], k = X[3], v = X[4];
+      const double kk = k - val[2];
+      if (col && ci < j) {
+        const double ds = (ci < j - 1) ? h * h * (double)(j - 1 - ci) : 0.0;
+        double nD, nO;
+        if (!cb) {
+          nD = dD + h * (v * dO);
+          nO = dO + h * (v * h);
+        } else {
+          nD = dD + h * (h * o + v * dO);
+          nO = dO + h * (h * kk - v * (slope[2] * ds));
+        }
+        dD = nD;
+        dO = nO;
+      }
+      X[0] = X[0] + h * v;
+      X[1] = d + h * (v * o);
+      X[2] = o + h * (v * kk);
+      X[3] = k + h * pb.U[2 * j];
+      X[4] = v + h * pb.U[2 * j + 1];
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < 2; ++m)
+    if (lane + 32 * m < NTRI) st.H[lane + 32 * m] = Hm[m];
+  __syncwarp();
+  // lane rows: offsets and norms (lane r < 8 takes row r), then q = g - H U on lanes 0..9
+  if (lane < N_LANE) {
+    const int jj = lane >> 1, L = 2 * (jj + 1), o = doff(jj);
+    double dU = 0.0, oU = 0.0, dd = 0.0, dox = 0.0, oo = 0.0;
+#pragma unroll
+    for (int cc = 0; cc < NV - 2; ++cc) {
+      if (cc < L) {
+        const double Dc = st.D[o + cc], Oc = st.O[o + cc], Uc = pb.U[cc];
+        dU = fma(Dc, Uc, dU);
+        oU = fma(Oc, Uc, oU);
+        dd = fma(Dc, Dc, dd);
+        dox = fma(Dc, Oc, dox);
+        oo = fma(Oc, Oc, oo);
+      }
+    }
+    const double al = (lane & 1) ? P.alpha_lane[2] : 0.0;
+    st.lane_c[lane] = (ws.xh[jj + 2][0] + al * ws.xh[jj + 2][1]) - (dU + al * oU);
+    const double n2 = dd + 2.0 * al * dox + al * al * oo;
+    st.lane_inrm[lane] = 1.0 / dmax(n2, NRM2_FLOOR);
+  }
+  if (col) {
+    double acc = g;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) acc = fma(-st.H[c >= j ? tri(c, j) : tri(j, c)], pb.U[j], acc);
+    st.q[c] = acc;
+  }
+  const_viol = cv;
+  __syncwarp();
+}
+
 template <bool FIRST_PASS>
 __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared& ws, int lane) {
   const unsigned FULL = 0xffffffffu;
@@ -140,7 +281,23 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 prologue, 1 linearise, 2 rows, 3 factor, 4 iterations, 5 round end
 #endif
   CPROF_T(tp0);
-  if (lane == 0) ws.iflag[0] = prologue(T, P, pb, st) ? 1 : 0;
+  // warm start: the five reference-control lookups (binary searches in the table) at once on five lanes
+  if (lane < NH) {
+    double s_cur = pb.x0[0], s_mine = pb.x0[0];
+#pragma unroll
+    for (int j = 0; j < NH; ++j) {
+      if (lane == j) s_mine = s_cur;
+      s_cur += pb.x0[4] * P.h;
+    }
+    int hint = 0;
+    double u2[2];
+    lookup_control(T, s_mine, u2, hint);
+    ws.ur[lane][0] = u2[0];
+    ws.ur[lane][1] = u2[1];
+    pb.hint[lane] = hint;
+  }
+  __syncwarp();
+  if (lane == 0) ws.iflag[0] = prologue(T, P, pb, st, ws.ur) ? 1 : 0;
   __syncwarp();
   CPROF_T(tp1);
   CPROF_ADD(0, tp0, tp1);
@@ -209,15 +366,11 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
 
   for (int round = 0; round < max_rounds && !done; ++round) {
     CPROF_T(tl0);
-    if (lane == 0) {
-      double cviol;
-      linearise(T, P, pb, st, cviol);
-      ws.scal[0] = cviol;
-    }
-    __syncwarp();
+    double cviol;
+    coop_linearise(T, P, ws, st, lane, ki, kj, cviol);
     CPROF_T(tl1);
     CPROF_ADD(1, tl0, tl1);
-    if (ws.scal[0] > P.feas_tol) { infeasible = true; out.const_infeasible = true; }
+    if (cviol > P.feas_tol) { infeasible = true; out.const_infeasible = true; }
     out.rounds++;
     // dense rows of this round
 #pragma unroll

@@ -68,6 +68,7 @@ struct DevParams {
   double alpha_lane[3];// 0, wheelbase/2, wheelbase
   double brake_lookahead, brake_guess;
   int max_rounds, fast_max_rounds;
+  int thread_max_rounds, thread_max_segments;   // two-level policy caps inside the thread-per-problem kernel
   int max_fail_rounds; // robust pass: give up after this many rounds whose QP did not close
   Policy pol[2];       // [0] robust ladder, [1] two-level (first pass)
   double eps_p, eps_d, eps_inf, step_tol, feas_tol;
@@ -190,6 +191,24 @@ MPCB_HD void warm_start(const DevTable& T, const DevParams& P, const double (&x0
     if (hints) hints[j] = hint;
     U[2 * j] = ur[0];
     U[2 * j + 1] = brake ? P.brake_guess : ur[1];
+    s_cur += v_cur * P.h;
+  }
+}
+
+// the same from reference controls looked up beforehand: ur[j] = get_control(s0 + j h v0) (warp-per-problem kernel,
+// where five lanes do the five lookups at once)
+MPCB_HD void warm_fill(const DevParams& P, const double (&x0)[5], const double (&obs)[2][2], int n_obs,
+                       const double (*ur)[2], double (&U)[NV]) {
+  double s_cur = x0[0];
+  const double v_cur = x0[4];
+  bool brake = false;
+#pragma unroll
+  for (int j = 0; j < NH; ++j) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+      if (k < n_obs && (obs[k][0] - s_cur) < P.brake_lookahead) brake = true;
+    U[2 * j] = ur[j][0];
+    U[2 * j + 1] = brake ? P.brake_guess : ur[j][1];
     s_cur += v_cur * P.h;
   }
 }

@@ -28,7 +28,7 @@ struct mpcb_ctx {
   // workspace for the host-buffer entry points
   void* ws = nullptr;
   size_t ws_bytes = 0;
-  int* fb = nullptr;          // [1 + fb_cap]: count, then indices of problems left to the second pass
+  int* fb = nullptr;          // work list(s): header (count, two cursors, pad), then indices of problems left to the second pass
   int fb_cap = 0;
   cudaStream_t stream = nullptr;   // private stream of the *_host entry points
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, ev_mid = nullptr;

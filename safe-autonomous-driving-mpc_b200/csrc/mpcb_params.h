@@ -30,6 +30,7 @@ inline void default_params(mpcb_params* p) {
   p->fast_rho_off = 1e-9; p->fast_rho_on = 1e6;
   p->fast_max_rounds = 6; p->fast_max_segments = 4; p->fast_segment_iters = 2;
   p->coop_pass2 = 1; p->coop_max_batch = 2048;
+  p->thread_max_rounds = 4; p->thread_max_segments = 2;
 }
 
 // mpcb_params -> constants of the kernels.  pol[0]: robust ladder (x10 per rung with hysteresis, alpha as given,
@@ -40,7 +41,7 @@ inline int derive_params(const mpcb_params& p, DevParams& d) {
   if (!(p.dt > 0) || p.max_rounds < 1 || p.max_segments < 1 || p.segment_iters < 1) return MPCB_ERR_INVALID;
   if (!(p.rho_lo > 0) || !(p.rho_hi >= p.rho_lo) || !(p.alpha > 0 && p.alpha < 2)) return MPCB_ERR_INVALID;
   if (!(p.fast_rho_off > 0) || !(p.fast_rho_on > p.fast_rho_off) || p.fast_max_rounds < 1 ||
-      p.fast_max_segments < 1 || p.fast_segment_iters < 1)
+      p.fast_max_segments < 1 || p.fast_segment_iters < 1 || p.thread_max_rounds < 1 || p.thread_max_segments < 1)
     return MPCB_ERR_INVALID;
   memset(&d, 0, sizeof(d));
   d.h = p.dt;
@@ -51,6 +52,8 @@ inline int derive_params(const mpcb_params& p, DevParams& d) {
   d.alpha_lane[0] = 0.0; d.alpha_lane[1] = p.wheelbase / 2.0; d.alpha_lane[2] = p.wheelbase;
   d.brake_lookahead = p.brake_lookahead; d.brake_guess = p.brake_guess;
   d.max_rounds = p.max_rounds; d.fast_max_rounds = p.fast_max_rounds;
+  d.thread_max_rounds = std::min(p.thread_max_rounds, p.fast_max_rounds);
+  d.thread_max_segments = std::min(p.thread_max_segments, p.fast_max_segments);
   // robust ladder
   Policy& r = d.pol[0];
   const double fac = 10.0;

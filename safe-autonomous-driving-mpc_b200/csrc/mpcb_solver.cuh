@@ -577,7 +577,8 @@ struct SolveOut { int status, rounds, iters; bool const_infeasible; };
 // can no longer keep the gap), and the problem is flagged infeasible at once instead of waiting for an ADMM certificate.  Also: table hints, warm start
 // (trajectory_tracking.py:223-246) clipped to the bounds as scipy does (_slsqp_py.py:322).  Returns "screened".
 template <class ST>
-MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const ST& st) {
+MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const ST& st,
+                      const double (*ur)[2] = nullptr) {   // ur: reference controls already looked up (pb.hint set)
   bool screened = false;
   double blo[NH], bhi[NH], bstop[NH];
   {
@@ -634,7 +635,8 @@ MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const 
   }
 #pragma unroll
   for (int i = 0; i < NH; ++i) { st.blo[i] = blo[i]; st.bhi[i] = bhi[i]; }
-  warm_start(T, P, pb.x0, pb.obs, pb.n_obs, pb.U, pb.hint);
+  if (ur) warm_fill(P, pb.x0, pb.obs, pb.n_obs, ur, pb.U);
+  else warm_start(T, P, pb.x0, pb.obs, pb.n_obs, pb.U, pb.hint);
   pb.hint[NH] = pb.hint[NH - 1];
 #pragma unroll
   for (int i = 0; i < NV; ++i) pb.U[i] = clipd(pb.U[i], P.umin[i & 1], P.umax[i & 1]);  // scipy clips x0 to the bounds
@@ -658,7 +660,8 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
   const Policy& pl = P.pol[FIRST_PASS ? 1 : 0];
   double step_prev = 1e30;
   int fails = 0;
-  const int max_rounds = FIRST_PASS ? P.fast_max_rounds : P.max_rounds;
+  const int max_rounds = FIRST_PASS ? P.thread_max_rounds : P.max_rounds;
+  const int max_segments = FIRST_PASS ? P.thread_max_segments : pl.max_segments;
   // cold ADMM state at x: z = clip(A x), y = 0  ->  v = z ; all rows on the initial rung of policy m
   auto cold_start = [&](const double (&xx)[NV]) {
 #pragma unroll
@@ -687,7 +690,7 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
     bool conv = false;                           // this round's QP closed
     bool qdone = done;                           // nothing more to do on this round's QP (closed, certified or caps hit)
     bool cert = false;
-    for (int seg = 0; seg < pl.max_segments; ++seg) {
+    for (int seg = 0; seg < max_segments; ++seg) {
       if (MPCB_ALL(qdone)) break;
       if (!qdone) {
         factor(P, pl, pb, st);

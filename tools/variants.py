@@ -6,8 +6,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
-    "ROWSPACE": [],
-    "NOROWSPACE": ["MPCB_COOP_ROWSPACE=0"],
+    "COOP2": ["MPCB_COOP_CTAS=2"],
+    "COOP3": ["MPCB_COOP_CTAS=3"],
+    "COOP4": ["MPCB_COOP_CTAS=4"],
     "T128_C2_M7": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7"],
     "T128_C2_M7_W": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
     "T64_C4_M7_W": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_MASK=7", "MPCB_WARP_UNIFORM=1"],
@@ -25,10 +26,10 @@ if sys.argv[1] == "build":
                               "-Xptxas", "-v", "-I", os.path.join(ROOT, "include"), "-I", b.CSRC, "-shared", "-Xcompiler",
                               "-fPIC", "-o", lib] + ["-D" + d for d in VARIANTS[n]] +
                              [os.path.join(b.CSRC, s) for s in b.SOURCES], capture_output=True, text=True)
-        info = [l for l in res.stderr.splitlines() if "solve_kernel" in l or "stack frame" in l or "Used" in l]
+        info = [l for l in res.stderr.splitlines() if "_kernel" in l or "stack frame" in l or "Used" in l]
         sel = []
         for i, l in enumerate(info):
-            if "solve_kernel" in l and "Function properties" in l:
+            if ("solve_kernel" in l or "coop_kernel" in l) and "Function properties" in l:
                 sel += [info[i + 1].strip(), info[i + 2].strip()]
         print(n, res.returncode, " | ".join(sel))
         if res.returncode != 0:
