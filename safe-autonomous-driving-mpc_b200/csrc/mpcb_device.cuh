@@ -133,27 +133,37 @@ MPCB_HD int seg_index_hint(const double* __restrict__ sa, int K, double x, int& 
   return i;
 }
 
+// The knots and rows of the hinted segment are loaded speculatively, all at once; when the hint is right (the usual
+// case) the lookup is ONE memory round trip instead of a chain of three (walk, knots, rows).
 MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], double (&slope)[4], int& hint) {
   if (s >= T.s_max) {
 #pragma unroll
     for (int c = 0; c < 4; ++c) { val[c] = T.last[c]; slope[c] = 0.0; }
     return;
   }
-  const int i = seg_index_hint(T.s, T.K, s, hint);
-  const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
-  const double inv = 1.0 / (x_hi - x_lo);
-  const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
+  int i = hint < 1 ? 1 : (hint > T.K - 1 ? T.K - 1 : hint);
+  double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   double ylo[4], yhi[4];
+  auto load_rows = [&](int ii) {
 #if defined(__CUDA_ARCH__)
-  {
-    const double2* yl = reinterpret_cast<const double2*>(T.y + 4 * (i - 1));
+    const double2* yl = reinterpret_cast<const double2*>(T.y + 4 * (ii - 1));
     const double2 l0 = __ldg(yl), l1 = __ldg(yl + 1), h0 = __ldg(yl + 2), h1 = __ldg(yl + 3);
     ylo[0] = l0.x; ylo[1] = l0.y; ylo[2] = l1.x; ylo[3] = l1.y;
     yhi[0] = h0.x; yhi[1] = h0.y; yhi[2] = h1.x; yhi[3] = h1.y;
-  }
 #else
-  for (int c = 0; c < 4; ++c) { ylo[c] = T.y[4 * (i - 1) + c]; yhi[c] = T.y[4 * i + c]; }
+    for (int c = 0; c < 4; ++c) { ylo[c] = T.y[4 * (ii - 1) + c]; yhi[c] = T.y[4 * ii + c]; }
 #endif
+  };
+  load_rows(i);
+  if (!((i == T.K - 1 || x_hi >= s) && (i == 1 || x_lo < s))) {   // hint off: walk / search, then load again
+    i = seg_index_hint(T.s, T.K, s, hint);
+    x_lo = MPCB_LDG(T.s + i - 1);
+    x_hi = MPCB_LDG(T.s + i);
+    load_rows(i);
+  }
+  hint = i;
+  const double inv = 1.0 / (x_hi - x_lo);
+  const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     val[c] = wl * yhi[c] + wr * ylo[c];

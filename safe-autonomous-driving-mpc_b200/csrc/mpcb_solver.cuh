@@ -389,22 +389,30 @@ struct AtAcc {
 // ------------------------------------------------------------------------------------------------
 // rho_r from the rungs, then K = H + A' diag(rho) A = L L'  (packed lower triangle, reciprocal diagonal kept)
 // ------------------------------------------------------------------------------------------------
-template <class ST>
+// TWO: the two-level policy (two rungs, no hysteresis, inactive rows drop at once).  Under it a row's rung after a
+// check is simply "was active in that check", i.e. the rung vector IS the bit mask act_prev: no 4-bit rung fields to
+// read, modify and write back, and the two step sizes are selected, not looked up.
+template <bool TWO, class ST>
 MPCB_HD void factor(const DevParams& P, const Policy& pl, Problem& pb, const ST& st) {
   const double h = P.h;
   // step sizes of this factorisation
+  const double lad0 = pl.lad[0], lad1 = pl.lad[1];
+  auto step_size = [&](int r) -> double {
+    if (TWO) return ((pb.act_prev >> r) & 1ull) ? lad1 : lad0;
+    return pl.lad[pb.E.get(r)];
+  };
 #pragma unroll
-  for (int i = 0; i < NV; ++i) st.rho[i] = pl.lad[pb.E.get(i)];
+  for (int i = 0; i < NV; ++i) st.rho[i] = step_size(i);
 #pragma unroll
-  for (int r = 0; r < N_LANE; ++r) st.rho[ROW_LANE + r] = pl.lad[pb.E.get(ROW_LANE + r)] * st.lane_inrm[r];
+  for (int r = 0; r < N_LANE; ++r) st.rho[ROW_LANE + r] = step_size(ROW_LANE + r) * st.lane_inrm[r];
 #pragma unroll
   for (int j = 1; j <= NH; ++j) {
-    st.rho[ROW_V + j - 1] = pl.lad[pb.E.get(ROW_V + j - 1)] * P.inrm_v[j - 1];
+    st.rho[ROW_V + j - 1] = step_size(ROW_V + j - 1) * P.inrm_v[j - 1];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const bool on = k < pb.n_obs;
-      if (j > 1) st.rho[row_r1(k, j)] = on ? pl.lad[pb.E.get(row_r1(k, j))] * P.inrm_r1[j - 1] : 0.0;
-      st.rho[row_r2(k, j)] = on ? pl.lad[pb.E.get(row_r2(k, j))] * P.inrm_r2[j - 1] : 0.0;
+      if (j > 1) st.rho[row_r1(k, j)] = on ? step_size(row_r1(k, j)) * P.inrm_r1[j - 1] : 0.0;
+      st.rho[row_r2(k, j)] = on ? step_size(row_r2(k, j)) * P.inrm_r2[j - 1] : 0.0;
     }
   }
   double K[NTRI];
@@ -493,7 +501,7 @@ struct SegStats { double rp, rd, nd, atdy, sup, bad; };
 // One ADMM iteration.
 //   CHECK = false: v += alpha (A x - clip(v)), nothing else.
 //   CHECK = true : additionally residuals, active set, step-size policy; CERT adds the infeasibility certificate.
-template <bool CHECK, bool CERT, class ST>
+template <bool CHECK, bool CERT, bool TWO, class ST>
 MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const ST& st, SegStats& stt) {
   const double relax = pl.relax;
   double rhs[NV];
@@ -538,10 +546,17 @@ MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const 
       acc2.add(r, dy);
     }
     // step-size policy
-    const int e = pb.E.get(r);
     const bool a_now = (vn < lo) || (vn > hi);
     const bool a_prev = (pb.act_prev >> r) & 1ull;
     double vnew = vn;
+    if (TWO) {
+      // rung = activity in the previous check; a row that turns active moves up: keep (z, y), v' = z + (rho/rho')(v - z)
+      if (a_now && !a_prev) vnew = fma(pl.lad_ratio[1], vn - zn, zn);
+      if (a_now) act |= (1ull << r);
+      st.v[r] = vnew;
+      return;
+    }
+    const int e = pb.E.get(r);
     if (a_now && (a_prev || !pl.hysteresis) && e < pl.n_rung - 1) {
       pb.E.set(r, e + 1);
       vnew = fma(pl.lad_ratio[e + 1], vn - zn, zn);   // keep (z, y): v' = z + (rho/rho') (v - z)
@@ -693,10 +708,10 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
     for (int seg = 0; seg < max_segments; ++seg) {
       if (MPCB_ALL(qdone)) break;
       if (!qdone) {
-        factor(P, pl, pb, st);
+        factor<FIRST_PASS>(P, pl, pb, st);
         SegStats s;
-        for (int it = 0; it < pl.segment_iters - 1; ++it) admm_iter<false, false>(P, pl, pb, st, s);
-        admm_iter<true, !FIRST_PASS>(P, pl, pb, st, s);
+        for (int it = 0; it < pl.segment_iters - 1; ++it) admm_iter<false, false, FIRST_PASS>(P, pl, pb, st, s);
+        admm_iter<true, !FIRST_PASS, FIRST_PASS>(P, pl, pb, st, s);
         out.iters += pl.segment_iters;
 #ifdef MPCB_TRACE
         if (getenv("MPCB_TRACE")) {

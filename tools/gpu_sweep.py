@@ -12,7 +12,7 @@ tab = P.RefTable.from_npz(f"{ROOT}/data/trajectory3.npz")
 x0, obs, n = P.monte_carlo_problems(tab, 65536)
 dx, do, dn = (torch.from_numpy(a).cuda() for a in (x0, obs, n))
 ref = None
-for rounds, segs, its in itertools.product((3, 4, 5, 6), (1, 2, 3, 4), (2,)):
+for rounds, segs, its in itertools.product((3, 4, 5), (1, 2, 3), (2, 3)):
     T = M.BatchedTracker(L, thread_max_rounds=rounds, thread_max_segments=segs, fast_segment_iters=its)
     out = T.solve_batch(dx, do, dn)
     torch.cuda.synchronize()
