@@ -75,8 +75,11 @@ typedef struct mpcb_params {
   /* tighter caps of the two-level policy inside the thread-per-problem kernel, where the slowest problem of a CTA
    * holds up the other 127: what these caps cut off goes to the second pass (one warp per problem, nobody waits)
    * like everything else the first pass does not certify */
-  int thread_max_rounds;           /* default 4 */
-  int thread_max_segments;         /* default 2 */
+  int thread_max_rounds;           /* default 5 */
+  int thread_max_segments;         /* default 1: one active-set update (two ADMM iterations) per linearisation */
+  int thread_fail_rounds;          /* rounds whose QP did not close within thread_max_segments that the first pass tolerates
+                                      (the ADMM state carries over: the active-set search continues on the next
+                                      linearisation; only a round with a closed QP and a small step certifies), default 3 */
 } mpcb_params;
 
 typedef struct mpcb_ctx* mpcb_handle;

@@ -34,7 +34,7 @@ class Params(C.Structure):
         ("fast_pass", C.c_int), ("fast_rho_off", C.c_double), ("fast_rho_on", C.c_double),
         ("fast_max_rounds", C.c_int), ("fast_max_segments", C.c_int), ("fast_segment_iters", C.c_int),
         ("coop_pass2", C.c_int), ("coop_max_batch", C.c_int),
-        ("thread_max_rounds", C.c_int), ("thread_max_segments", C.c_int),
+        ("thread_max_rounds", C.c_int), ("thread_max_segments", C.c_int), ("thread_fail_rounds", C.c_int),
     ]
 
 

@@ -70,6 +70,8 @@ struct DevParams {
   int max_rounds, fast_max_rounds;
   int thread_max_rounds, thread_max_segments;   // two-level policy caps inside the thread-per-problem kernel
   int max_fail_rounds; // robust pass: give up after this many rounds whose QP did not close
+  int fast_fail_rounds;// first pass (thread kernel): rounds whose QP did not close that are tolerated (the ADMM state
+                       // carries over, so the active-set search simply continues on the next linearisation)
   Policy pol[2];       // [0] robust ladder, [1] two-level (first pass)
   double eps_p, eps_d, eps_inf, step_tol, feas_tol;
   double qp_forcing, qp_eps_loose;   // robust pass: QP tolerance of a round = clamp(forcing * previous SQP step, eps, loose)

@@ -30,7 +30,7 @@ inline void default_params(mpcb_params* p) {
   p->fast_rho_off = 1e-9; p->fast_rho_on = 1e6;
   p->fast_max_rounds = 6; p->fast_max_segments = 4; p->fast_segment_iters = 2;
   p->coop_pass2 = 1; p->coop_max_batch = 2048;
-  p->thread_max_rounds = 4; p->thread_max_segments = 2;
+  p->thread_max_rounds = 5; p->thread_max_segments = 1; p->thread_fail_rounds = 3;
 }
 
 // mpcb_params -> constants of the kernels.  pol[0]: robust ladder (x10 per rung with hysteresis, alpha as given,
@@ -85,9 +85,11 @@ inline int derive_params(const mpcb_params& p, DevParams& d) {
   d.step_tol = p.step_tol; d.feas_tol = p.feas_tol;
   d.qp_forcing = 1e-3; d.qp_eps_loose = 1e-4;
   d.max_fail_rounds = 2;
+  d.fast_fail_rounds = p.thread_fail_rounds < 0 ? 0 : p.thread_fail_rounds;
 #ifndef __CUDACC__
   if (getenv("MPCB_FORCING")) d.qp_forcing = atof(getenv("MPCB_FORCING"));
   if (getenv("MPCB_MAXFAIL")) d.max_fail_rounds = atoi(getenv("MPCB_MAXFAIL"));
+  if (getenv("MPCB_FASTFAIL")) d.fast_fail_rounds = atoi(getenv("MPCB_FASTFAIL"));
 #endif
   const double h = p.dt, floor_ = NRM2_FLOOR;
   for (int j = 1; j <= NH; ++j) {

@@ -734,9 +734,12 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
       step_prev = step;
       if (cert) { infeasible = true; done = true; }
       else if (conv && step < P.step_tol) { done = true; out.status = 0; }
-      else if (!conv && FIRST_PASS) done = true;   // first pass: a QP it cannot close goes to the robust pass
-      else if (!conv && ++fails >= P.max_fail_rounds) done = true;   // robust pass: QPs that never close (status 1, or
-                                                                      // 2 through the final constraint check)
+      else if (!conv) {
+        // first pass: a QP it cannot close goes to the robust pass (after fast_fail_rounds tolerated ones);
+        // robust pass: QPs that never close end as status 1, or 2 through the final constraint check
+        ++fails;
+        if (FIRST_PASS ? fails > P.fast_fail_rounds : fails >= P.max_fail_rounds) done = true;
+      }
     }
   }
   // an infeasibility verdict is final only on a point the pass actually converged to (or, in the robust pass, gave

@@ -12,12 +12,12 @@ tab = P.RefTable.from_npz(f"{ROOT}/data/trajectory3.npz")
 x0, obs, n = P.monte_carlo_problems(tab, 65536)
 dx, do, dn = (torch.from_numpy(a).cuda() for a in (x0, obs, n))
 ref = None
-for rounds, segs, its in itertools.product((3, 4, 5), (1, 2, 3), (2, 3)):
-    T = M.BatchedTracker(L, thread_max_rounds=rounds, thread_max_segments=segs, fast_segment_iters=its)
+for rounds, segs, its in itertools.product((5, 6, 7, 8), (1,), (3, 4, 5, 7)):
+    T = M.BatchedTracker(L, thread_max_rounds=rounds, thread_max_segments=segs, thread_fail_rounds=its)
     out = T.solve_batch(dx, do, dn)
     torch.cuda.synchronize()
     best = 1e9
-    for rep in range(5):
+    for rep in range(8):
         T.solve_batch(dx, do, dn, out=out)
         torch.cuda.synchronize()
         if T.last_kernel_ms() < best:
@@ -27,5 +27,5 @@ for rounds, segs, its in itertools.product((3, 4, 5), (1, 2, 3), (2, 3)):
         pass
     if (rounds, segs, its) == (6, 4, 2):
         ref = (st.copy(), U.copy())
-    print(f"rounds {rounds} segs {segs} iters {its}: {best:.3f} ms  passes {passes[0]:.3f} + {passes[1]:.3f} ({passes[2]})  status {np.bincount(st, minlength=3)}", flush=True)
+    print(f"rounds {rounds} segs {segs} fails {its}: {best:.3f} ms  passes {passes[0]:.3f} + {passes[1]:.3f} ({passes[2]})  status {np.bincount(st, minlength=3)}", flush=True)
     del T
