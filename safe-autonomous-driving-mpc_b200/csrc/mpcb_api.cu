@@ -485,6 +485,21 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   }
   c->dt.s = c->d_s; c->dt.y = c->d_y; c->dt.u = c->d_u;
   c->dt.K = K; c->dt.Ku = c->Ku; c->dt.s_max = t->s_max;
+  {
+    // bucket index for lookups that have no previous segment to start from (first probe of the warm start, planner)
+    const int n = 4096;
+    const double s0 = t->s[0], span = t->s[K - 1] - t->s[0];
+    std::vector<int> lut(n);
+    const double scale = span > 0 ? (double)n / span : 0.0;
+    for (int b = 0; b < n; ++b) {
+      const double edge = s0 + (scale > 0 ? (double)b / scale : 0.0);
+      const int lo = (int)(std::lower_bound(t->s.begin(), t->s.end(), edge) - t->s.begin());
+      lut[b] = std::min(std::max(lo, 1), K - 1);
+    }
+    if (cudaMalloc(&c->d_lut, sizeof(int) * n) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    if ((e = cudaMemcpy(c->d_lut, lut.data(), sizeof(int) * n, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
+    c->dt.lut = c->d_lut; c->dt.lut_n = n; c->dt.lut_s0 = s0; c->dt.lut_scale = scale;
+  }
   for (int k = 0; k < 4; ++k) c->dt.last[k] = t->last_row[1 + k];
   *out = c;
   return MPCB_OK;
@@ -496,6 +511,7 @@ int mpcb_destroy(mpcb_handle h) {
   if (h->d_s) cudaFree(h->d_s);
   if (h->d_y) cudaFree(h->d_y);
   if (h->d_u) cudaFree(h->d_u);
+  if (h->d_lut) cudaFree(h->d_lut);
   if (h->ws) cudaFree(h->ws);
   if (h->fb) cudaFree(h->fb);
   if (h->ev0) cudaEventDestroy(h->ev0);

@@ -441,12 +441,18 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
 #pragma unroll
         for (int j = 0; j <= i; ++j) F.L[tri(i, j)] = ws.K[i][j];
       chol_regs(F);
+      const bool two = pb.n_obs == 2;     // rows 32..40 are exactly the second obstacle's: no second rows without it
 #pragma unroll
       for (int k = 0; k < CW_K; ++k) {
-        double t[NV];
+        if (k == 0 || two) {
+          double t[NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) t[i] = a[k][i];
-        chol_solve(F, t, g[k]);
+          for (int i = 0; i < NV; ++i) t[i] = a[k][i];
+          chol_solve(F, t, g[k]);
+        } else {
+#pragma unroll
+          for (int i = 0; i < NV; ++i) g[k][i] = 0.0;
+        }
       }
       double zt0_last = 0.0;
       // ---- iterations ---------------------------------------------------------------------------------------------
@@ -472,8 +478,10 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
 #pragma unroll
         for (int k = 0; k < CW_K; ++k) {
           double acc = 0.0, accb = 0.0;
+          if (k == 0 || two) {
 #pragma unroll
-          for (int i = 0; i < NV; i += 2) { acc = fma(g[k][i], rhs[i], acc); accb = fma(g[k][i + 1], rhs[i + 1], accb); }
+            for (int i = 0; i < NV; i += 2) { acc = fma(g[k][i], rhs[i], acc); accb = fma(g[k][i + 1], rhs[i + 1], accb); }
+          }
           zt[k] = acc + accb;
         }
         zt0_last = zt[0];

@@ -46,6 +46,10 @@ struct DevTable {
   int K, Ku;
   double s_max;
   double last[4];    // X_ref[-1][1:5], returned for s >= s_max
+  // optional bucket index over [s[0], s[K-1]]: lut[b] = segment of the left edge of bucket b (nullptr: binary search)
+  const int* lut;
+  int lut_n;
+  double lut_s0, lut_scale;
 };
 
 // Step-size policy of the ADMM machinery (mpcb_solver.cuh).
@@ -137,6 +141,17 @@ MPCB_HD int seg_index_hint(const double* __restrict__ sa, int K, double x, int& 
 
 // The knots and rows of the hinted segment are loaded speculatively, all at once; when the hint is right (the usual
 // case) the lookup is ONE memory round trip instead of a chain of three (walk, knots, rows).
+// seg_index without a previous segment to walk from: the bucket index gives a first guess that is at most a knot or
+// two off, the walk of seg_index_hint does the rest (13 dependent loads of the binary search -> 2 or 3).
+MPCB_HD int seg_index_cold(const DevTable& T, int K, double x) {
+  if (!T.lut) return seg_index(T.s, K, x);
+  double t = (x - T.lut_s0) * T.lut_scale;
+  t = t > 0.0 ? t : 0.0;                                // also catches NaN
+  t = t < (double)(T.lut_n - 1) ? t : (double)(T.lut_n - 1);
+  int hint = MPCB_LDG(T.lut + (int)t);
+  return seg_index_hint(T.s, K, x, hint);
+}
+
 MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], double (&slope)[4], int& hint) {
   if (s >= T.s_max) {
 #pragma unroll
@@ -175,7 +190,7 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
 
 MPCB_HD void lookup_control(const DevTable& T, double s, double (&u)[2], int& hint) {
   if (s >= T.s_max) { u[0] = 0.0; u[1] = 0.0; return; }
-  const int i = (hint > 0) ? seg_index_hint(T.s, T.Ku, s, hint) : (hint = seg_index(T.s, T.Ku, s));
+  const int i = (hint > 0) ? seg_index_hint(T.s, T.Ku, s, hint) : (hint = seg_index_cold(T, T.Ku, s));
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
   const double ul0 = MPCB_LDG(T.u + 2 * (i - 1)), ul1 = MPCB_LDG(T.u + 2 * (i - 1) + 1);

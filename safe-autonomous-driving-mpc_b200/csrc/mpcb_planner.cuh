@@ -33,7 +33,7 @@ struct PlanParams {
 
 // interp_k(s): value and slope of the bracketing segment (no s >= s_max clamp: this is the raw interpolator)
 MPCB_HD void lookup_kref(const DevTable& T, double s, double& kap, double& dkap) {
-  const int i = seg_index(T.s, T.K, s);
+  const int i = seg_index_cold(T, T.K, s);
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double y_lo = MPCB_LDG(T.y + 4 * (i - 1) + 2), y_hi = MPCB_LDG(T.y + 4 * i + 2);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);

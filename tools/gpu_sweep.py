@@ -12,8 +12,13 @@ tab = P.RefTable.from_npz(f"{ROOT}/data/trajectory3.npz")
 x0, obs, n = P.monte_carlo_problems(tab, 65536)
 dx, do, dn = (torch.from_numpy(a).cuda() for a in (x0, obs, n))
 ref = None
-for rounds, segs, its in itertools.product((5, 6, 7, 8), (1,), (3, 4, 5, 7)):
-    T = M.BatchedTracker(L, thread_max_rounds=rounds, thread_max_segments=segs, thread_fail_rounds=its)
+SWEEP = os.environ.get("SWEEP", "thread")
+grid = itertools.product((5, 6), (1, 2, 3), (3, 5)) if SWEEP == "thread" else itertools.product((4, 5, 6, 8, 10, 15), (0,), (1.5, 1.6, 1.7))
+for rounds, segs, its in grid:
+    if SWEEP == "thread":
+        T = M.BatchedTracker(L, thread_max_rounds=rounds, thread_max_segments=1, fast_segment_iters=segs, thread_fail_rounds=its)
+    else:
+        T = M.BatchedTracker(L, segment_iters=rounds, max_segments=max(1, 120 // rounds), alpha=its)
     out = T.solve_batch(dx, do, dn)
     torch.cuda.synchronize()
     best = 1e9

@@ -6,6 +6,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
+    "T128_C2_M13": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=13"],
+    "T128_C2_M9": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=9"],
+    "T128_C2_M37": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=37"],
+    "T128_C2_M133": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=133"],
+    "T64_C4_M7": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=4", "MPCB_STORE_MASK=7"],
+    "T128_C2_M3": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=3"],
+    "T128_C2_M5": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=5"],
+    "T128_C2_M135": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=135"],
+    "T256_C1_M7": ["MPCB_SOLVE_THREADS=256", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_MASK=7"],
+    "T96_C3_M1": ["MPCB_SOLVE_THREADS=96", "MPCB_SOLVE_CTAS=3", "MPCB_STORE_MASK=1"],
     "COOP2": ["MPCB_COOP_CTAS=2"],
     "COOP3": ["MPCB_COOP_CTAS=3"],
     "COOP4": ["MPCB_COOP_CTAS=4"],
