@@ -478,6 +478,12 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   if ((e = cudaEventCreate(&c->ev0)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev_mid)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
+  if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
+  if ((e = cudaFuncSetAttribute(mpcb_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(mpcb_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(mpcb_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM)) != cudaSuccess ||
+      (e = cudaFuncSetAttribute(mpcb_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM)) != cudaSuccess)
+    return fail(cuda_fail(e, "cudaFuncSetAttribute"));
   c->xs[0] = c->stream;
   for (int k = 1; k < 4; ++k) {
     if ((e = cudaStreamCreateWithPriority(&c->xs[k], cudaStreamNonBlocking, std::min(prio_lo, prio_hi + k))) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate"));
@@ -512,6 +518,11 @@ int mpcb_destroy(mpcb_handle h) {
   if (h->d_y) cudaFree(h->d_y);
   if (h->d_u) cudaFree(h->d_u);
   if (h->d_lut) cudaFree(h->d_lut);
+  for (int k = 0; k < 2; ++k) {
+    if (h->gslot[k].exec) cudaGraphExecDestroy(h->gslot[k].exec);
+    if (h->gslot[k].graph) cudaGraphDestroy(h->gslot[k].graph);
+  }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ws) cudaFree(h->ws);
   if (h->fb) cudaFree(h->fb);
   if (h->ev0) cudaEventDestroy(h->ev0);
@@ -529,7 +540,10 @@ int mpcb_destroy(mpcb_handle h) {
 
 // ---- solve ---------------------------------------------------------------------------------------
 // fallback-list storage for a batch of B problems split into up to HOST_CHUNKS independently launched parts
-static const int HOST_CHUNKS = 4;
+#ifndef MPCB_HOST_CHUNKS
+#define MPCB_HOST_CHUNKS 4
+#endif
+static const int HOST_CHUNKS = MPCB_HOST_CHUNKS;   // parts of a large host batch, dealt round-robin onto the 4 streams
 static int ensure_fb(mpcb_handle h, int B) {
   if (!h->params.fast_pass || B + FB_HDR * HOST_CHUNKS <= h->fb_cap) return MPCB_OK;
   if (h->fb) { CK(cudaFree(h->fb)); h->fb = nullptr; h->fb_cap = 0; }
@@ -544,10 +558,6 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
                         double* Xpred_out, double* obj_out, int* status_out, int* iters_out, double* cmin_out,
                         unsigned long long* active_out, cudaStream_t st, int* fb, bool timed, bool whole_call = true) {
   const int grid = (B + SOLVE_THREADS - 1) / SOLVE_THREADS;
-  CK(cudaFuncSetAttribute(mpcb_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
-  CK(cudaFuncSetAttribute(mpcb_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM));
-  CK(cudaFuncSetAttribute(mpcb_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM));
-  CK(cudaFuncSetAttribute(mpcb_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM));
   if (timed) CK(cudaEventRecord(h->ev0, st));
   if (h->params.fast_pass) {
     int* fb_count = fb;
@@ -569,7 +579,10 @@ static int launch_solve(mpcb_handle h, int B, const double* x0, const double* ob
     // second pass over whatever the first did not certify
     if (h->params.coop_pass2) {
       // one warp per problem: the leftovers are few and hard, what matters is their latency
-      const int g2 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * COOP_CTAS);
+      // (after a thread-per-problem first pass a few per cent of the problems are left: a grid sized for that, so that
+      // the parts of a chunked host call do not queue whole grids of idle CTAs behind each other's first passes)
+      const bool small = whole_call && B <= h->params.coop_max_batch;
+      const int g2 = std::min(h->n_sm * COOP_CTAS, small ? (B + COOP_WARPS - 1) / COOP_WARPS : std::max(16, (B + 63) / 64));
       mpcb_coop_kernel<false><<<g2, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs, U_out,
                                                              Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
                                                              nullptr, nullptr, fb + 2);
@@ -649,25 +662,133 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
   double* dcm = cmin_out ? (double*)(w + o_cm) : nullptr;
   unsigned long long* dac = active_out ? (unsigned long long*)(w + o_ac) : nullptr;
 
-  if (B <= HOST_PACKED_MAX) {
-    if (total > h->pin_bytes) {
-      if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_bytes = 0; }
-      size_t want = total;
-      { const size_t nmax = HOST_PACKED_MAX; want = std::max(want, (size_t)(al256(nmax * 40) + al256(nmax * 32) + 2 * al256(nmax * 4) + al256(nmax * 80) + al256(nmax * 240) + 4 * al256(nmax * 8))); }
-      if (cudaHostAlloc(&h->pin, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
-      h->pin_bytes = want;
+  // ---- graph replay / capture bookkeeping --------------------------------------------------------------------
+  const bool packed = B <= HOST_PACKED_MAX;
+  if (packed && total > h->pin_bytes) {
+    if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_bytes = 0; }
+    size_t want = total;
+    { const size_t nmax = HOST_PACKED_MAX; want = std::max(want, (size_t)(al256(nmax * 40) + al256(nmax * 32) + 2 * al256(nmax * 4) + al256(nmax * 80) + al256(nmax * 240) + 4 * al256(nmax * 8))); }
+    if (cudaHostAlloc(&h->pin, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
+    h->pin_bytes = want;
+  }
+  mpcb_ctx::GraphSlot& g = h->gslot[packed ? 0 : 1];
+  // everything the enqueued work depends on: batch size, which outputs are wanted, the library's own buffers, and
+  // (chunked path: the copies go straight from / to the caller's arrays) the caller's pointers
+  unsigned long long key[14] = {(unsigned long long)B, (unsigned long long)(size_t)h->ws, (unsigned long long)(size_t)h->fb,
+                                (unsigned long long)(size_t)h->pin,
+                                (unsigned long long)((Xpred_out != nullptr) | ((obj_out != nullptr) << 1) | ((status_out != nullptr) << 2) |
+                                                     ((iters_out != nullptr) << 3) | ((cmin_out != nullptr) << 4) | ((active_out != nullptr) << 5)),
+                                0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (!packed) {
+    const void* up[9] = {x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out};
+    for (int k = 0; k < 9; ++k) key[5 + k] = (unsigned long long)(size_t)up[k];
+    key[4] ^= (unsigned long long)(size_t)active_out << 8;
+  }
+  const bool hit = g.valid && memcmp(g.key, key, sizeof(key)) == 0;
+  bool capture = false;
+  if (!hit) {
+    capture = g.have_last && memcmp(g.last, key, sizeof(key)) == 0;     // second call in a row with these buffers
+    if (capture && !packed) {
+      // a graph replays the copies asynchronously: only for page-locked caller buffers
+      const void* up[10] = {x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out};
+      for (int k = 0; k < 10 && capture; ++k) {
+        if (!up[k]) continue;
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, up[k]) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); capture = false; }
+      }
     }
+    memcpy(g.last, key, sizeof(key));
+    g.have_last = true;
+  }
+  cudaStream_t s0 = h->xs[0];
+
+  // the device work of one call (the packed path keeps its per-pass timing events: in a graph they are event nodes)
+  auto enqueue = [&]() -> int {
+    if (packed) {
+      char* p = (char*)h->pin;
+      CK(cudaMemcpyAsync(w, p, o_U, cudaMemcpyHostToDevice, s0));
+      int r = launch_solve(h, B, (double*)(w + o_x0), (double*)(w + o_obs), (int*)(w + o_n), dU, dX, dobj, dst, dit, dcm, dac,
+                           s0, h->fb, true);
+      if (r != MPCB_OK) return r;
+      CK(cudaMemcpyAsync(p + o_U, w + o_U, total - o_U, cudaMemcpyDeviceToHost, s0));
+      return MPCB_OK;
+    }
+    // chunked, one stream per part
+    CK(cudaEventRecord(h->ev_fork, s0));
+    for (int c = 0; c < HOST_CHUNKS; ++c) {
+      const size_t lo = nb * c / HOST_CHUNKS, hi = nb * (c + 1) / HOST_CHUNKS, n = hi - lo;
+      if (n == 0) continue;
+      cudaStream_t st = h->xs[c % 4];
+      if (c > 0 && c < 4) CK(cudaStreamWaitEvent(st, h->ev_fork, 0));
+      CK(cudaMemcpyAsync(w + o_x0 + lo * 40, x0 + lo * 5, n * 40, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(w + o_obs + lo * 32, obs_sv + lo * 4, n * 32, cudaMemcpyHostToDevice, st));
+      CK(cudaMemcpyAsync(w + o_n + lo * 4, n_obs + lo, n * 4, cudaMemcpyHostToDevice, st));
+      int r = launch_solve(h, (int)n, (double*)(w + o_x0) + lo * 5, (double*)(w + o_obs) + lo * 4, (int*)(w + o_n) + lo,
+                           dU + lo * 10, dX ? dX + lo * 30 : nullptr, dobj ? dobj + lo : nullptr, dst ? dst + lo : nullptr,
+                           dit ? dit + lo * 2 : nullptr, dcm ? dcm + lo : nullptr, dac ? dac + lo : nullptr, st,
+                           h->fb + lo + FB_HDR * c, false, false);
+      if (r != MPCB_OK) return r;
+      CK(cudaMemcpyAsync(U_out + lo * 10, dU + lo * 10, n * 80, cudaMemcpyDeviceToHost, st));
+      if (Xpred_out) CK(cudaMemcpyAsync(Xpred_out + lo * 30, dX + lo * 30, n * 240, cudaMemcpyDeviceToHost, st));
+      if (obj_out) CK(cudaMemcpyAsync(obj_out + lo, dobj + lo, n * 8, cudaMemcpyDeviceToHost, st));
+      if (status_out) CK(cudaMemcpyAsync(status_out + lo, dst + lo, n * 4, cudaMemcpyDeviceToHost, st));
+      if (iters_out) CK(cudaMemcpyAsync(iters_out + lo * 2, dit + lo * 2, n * 8, cudaMemcpyDeviceToHost, st));
+      if (cmin_out) CK(cudaMemcpyAsync(cmin_out + lo, dcm + lo, n * 8, cudaMemcpyDeviceToHost, st));
+      if (active_out) CK(cudaMemcpyAsync(active_out + lo, dac + lo, n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    for (int c = 1; c < 4 && c < HOST_CHUNKS; ++c) {   // join
+      CK(cudaEventRecord(h->xe[c], h->xs[c]));
+      CK(cudaStreamWaitEvent(s0, h->xe[c], 0));
+    }
+    return MPCB_OK;
+  };
+
+  if (packed) {
     char* p = (char*)h->pin;
-    cudaStream_t st = h->stream;
     memcpy(p + o_x0, x0, nb * 40);
     memcpy(p + o_obs, obs_sv, nb * 32);
     memcpy(p + o_n, n_obs, nb * 4);
-    CK(cudaMemcpyAsync(w, p, o_U, cudaMemcpyHostToDevice, st));
-    rc = launch_solve(h, B, (double*)(w + o_x0), (double*)(w + o_obs), (int*)(w + o_n), dU, dX, dobj, dst, dit, dcm, dac,
-                      st, h->fb, true);
+  }
+  if (capture) {
+    // capture this call's work (nothing executes yet), instantiate, and fall through to the replay
+    if (g.exec) { cudaGraphExecDestroy(g.exec); g.exec = nullptr; }
+    if (g.graph) { cudaGraphDestroy(g.graph); g.graph = nullptr; }
+    g.valid = false;
+    const unsigned long long l0 = h->launches;
+    bool ok = cudaStreamBeginCapture(s0, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
+    if (ok) {
+      const int r = enqueue();
+      cudaGraph_t gr = nullptr;
+      const cudaError_t ee = cudaStreamEndCapture(s0, &gr);
+      ok = (r == MPCB_OK) && ee == cudaSuccess && gr != nullptr;
+      if (ok) ok = cudaGraphInstantiate(&g.exec, gr, 0) == cudaSuccess;
+      if (ok) { g.graph = gr; g.launches = h->launches - l0; memcpy(g.key, key, sizeof(key)); g.valid = true; }
+      else if (gr) cudaGraphDestroy(gr);
+    }
+    h->launches = l0;
+    if (!ok) cudaGetLastError();              // capture not possible here: enqueue directly below
+  }
+  if (g.valid && memcmp(g.key, key, sizeof(key)) == 0) {
+    if (!packed) CK(cudaEventRecord(h->ev0, s0));
+    CK(cudaGraphLaunch(g.exec, s0));
+    if (!packed) CK(cudaEventRecord(h->ev1, s0));
+    h->launches += g.launches;
+    h->timed = true;           // mpcb_last_kernel_ms: chunked path = device span of the whole call (copies included)
+    h->pass_timed = packed;
+    h->fb_last = h->fb;
+  } else {
+    if (!packed) CK(cudaEventRecord(h->ev0, s0));
+    rc = enqueue();
     if (rc != MPCB_OK) return rc;
-    CK(cudaMemcpyAsync(p + o_U, w + o_U, total - o_U, cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
+    if (!packed) {
+      CK(cudaEventRecord(h->ev1, s0));
+      h->timed = true;
+      h->pass_timed = false;
+    }
+  }
+  CK(cudaStreamSynchronize(s0));
+  if (packed) {
+    char* p = (char*)h->pin;
     memcpy(U_out, p + o_U, nb * 80);
     if (Xpred_out) memcpy(Xpred_out, p + o_X, nb * 240);
     if (obj_out) memcpy(obj_out, p + o_obj, nb * 8);
@@ -675,40 +796,7 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
     if (iters_out) memcpy(iters_out, p + o_it, nb * 8);
     if (cmin_out) memcpy(cmin_out, p + o_cm, nb * 8);
     if (active_out) memcpy(active_out, p + o_ac, nb * 8);
-    return MPCB_OK;
   }
-
-  // chunked, one stream per part
-  CK(cudaEventRecord(h->ev0, h->xs[0]));
-  for (int c = 0; c < HOST_CHUNKS; ++c) {
-    const size_t lo = nb * c / HOST_CHUNKS, hi = nb * (c + 1) / HOST_CHUNKS, n = hi - lo;
-    if (n == 0) continue;
-    cudaStream_t st = h->xs[c];
-    if (c > 0) CK(cudaStreamWaitEvent(st, h->ev0, 0));
-    CK(cudaMemcpyAsync(w + o_x0 + lo * 40, x0 + lo * 5, n * 40, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(w + o_obs + lo * 32, obs_sv + lo * 4, n * 32, cudaMemcpyHostToDevice, st));
-    CK(cudaMemcpyAsync(w + o_n + lo * 4, n_obs + lo, n * 4, cudaMemcpyHostToDevice, st));
-    rc = launch_solve(h, (int)n, (double*)(w + o_x0) + lo * 5, (double*)(w + o_obs) + lo * 4, (int*)(w + o_n) + lo,
-                      dU + lo * 10, dX ? dX + lo * 30 : nullptr, dobj ? dobj + lo : nullptr, dst ? dst + lo : nullptr,
-                      dit ? dit + lo * 2 : nullptr, dcm ? dcm + lo : nullptr, dac ? dac + lo : nullptr, st,
-                      h->fb + lo + FB_HDR * c, false, false);
-    if (rc != MPCB_OK) return rc;
-    CK(cudaMemcpyAsync(U_out + lo * 10, dU + lo * 10, n * 80, cudaMemcpyDeviceToHost, st));
-    if (Xpred_out) CK(cudaMemcpyAsync(Xpred_out + lo * 30, dX + lo * 30, n * 240, cudaMemcpyDeviceToHost, st));
-    if (obj_out) CK(cudaMemcpyAsync(obj_out + lo, dobj + lo, n * 8, cudaMemcpyDeviceToHost, st));
-    if (status_out) CK(cudaMemcpyAsync(status_out + lo, dst + lo, n * 4, cudaMemcpyDeviceToHost, st));
-    if (iters_out) CK(cudaMemcpyAsync(iters_out + lo * 2, dit + lo * 2, n * 8, cudaMemcpyDeviceToHost, st));
-    if (cmin_out) CK(cudaMemcpyAsync(cmin_out + lo, dcm + lo, n * 8, cudaMemcpyDeviceToHost, st));
-    if (active_out) CK(cudaMemcpyAsync(active_out + lo, dac + lo, n * 8, cudaMemcpyDeviceToHost, st));
-    if (c > 0) {
-      CK(cudaEventRecord(h->xe[c], st));
-      CK(cudaStreamWaitEvent(h->xs[0], h->xe[c], 0));
-    }
-  }
-  CK(cudaEventRecord(h->ev1, h->xs[0]));
-  h->timed = true;           // mpcb_last_kernel_ms: device span of the whole pipeline (copies included)
-  h->pass_timed = false;
-  CK(cudaStreamSynchronize(h->xs[0]));
   return MPCB_OK;
 }
 

@@ -41,4 +41,14 @@ struct mpcb_ctx {
   bool timed = false;
   bool pass_timed = false;
   unsigned long long launches = 0;
+  // CUDA graphs of the host-buffer entry point: the second call with the same batch size and the same buffers is
+  // captured, later ones are one cudaGraphLaunch instead of ~50 enqueue calls.  [0] packed small-batch path, [1] chunked
+  struct GraphSlot {
+    bool valid = false, have_last = false;
+    unsigned long long key[14] = {0}, last[14] = {0};
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    unsigned long long launches = 0;
+  } gslot[2];
+  cudaEvent_t ev_fork = nullptr;
 };

@@ -23,11 +23,16 @@ for l in sass[lo:hi]:
     m = re.match(r"\s+/\*([0-9a-f]+)\*/\s+(.*?);", l)
     if m:
         seq.append((int(m.group(1), 16), m.group(2).strip(), cur))
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["--kernel-name", "regex:" + os.environ["KREGEX"]] if "KREGEX" in os.environ else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
+secs = [k for k, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+want = [k for k in range(len(secs) - 1) if kname.split("ILb")[0].split("_kernel")[0] in rows[secs[k]][1]
+        and ("(bool)" + kname.split("ILb")[1][0] in rows[secs[k]][1] if "ILb" in kname else True)]
+k0 = want[int(os.environ.get("SECTION", "0"))]
+rows = rows[secs[k0]:secs[k0 + 1]]
 hdr, data = rows[1], rows[2:]
 assert len(data) == len(seq), (len(data), len(seq))
-iS, iE, iSel = hdr.index("# Samples"), hdr.index("Instructions Executed"), hdr.index("stall_selected")
+iS, iE, iSel = hdr.index(os.environ.get("COL", "# Samples")), hdr.index("Instructions Executed"), hdr.index("stall_selected")
 by, ex, n, issued = collections.Counter(), collections.Counter(), collections.Counter(), collections.Counter()
 for k, r in enumerate(data):
     ln = seq[k][2]

@@ -6,6 +6,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "build", "variants")
 VARIANTS = {
+    "HC1": ["MPCB_HOST_CHUNKS=1"], "HC2": ["MPCB_HOST_CHUNKS=2"], "HC3": ["MPCB_HOST_CHUNKS=3"], "HC4": ["MPCB_HOST_CHUNKS=4"],
+    "HC6": ["MPCB_HOST_CHUNKS=6"], "HC8": ["MPCB_HOST_CHUNKS=8"],
+    "T128_C1_M189": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_MASK=189"],
+    "T64_C2_M189": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=189"],
+    "T96_C1_M191": ["MPCB_SOLVE_THREADS=96", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_MASK=191"],
+    "T64_C2_M191": ["MPCB_SOLVE_THREADS=64", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_MASK=255"],
+    "T128_C1_M29": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_MASK=29"],
+    "T192_C1_M21": ["MPCB_SOLVE_THREADS=192", "MPCB_SOLVE_CTAS=1", "MPCB_STORE_MASK=21"],
     "T128_C2_M13": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=13"],
     "T128_C2_M9": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=9"],
     "T128_C2_M37": ["MPCB_SOLVE_THREADS=128", "MPCB_SOLVE_CTAS=2", "MPCB_STORE_MASK=37"],
@@ -47,6 +55,6 @@ if sys.argv[1] == "build":
 else:
     for n in (sys.argv[2:] or list(VARIANTS)):
         env = dict(os.environ, MPCB_LIB=os.path.join(OUT, n + ".so"))
-        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gpu_quick.py")], env=env, capture_output=True, text=True)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", os.environ.get("VTOOL", "gpu_quick.py"))], env=env, capture_output=True, text=True)
         lines = r.stdout.strip().splitlines()
-        print(n, lines[-1] if lines else r.stderr[-500:])
+        print(n, " || ".join(l for l in lines if l.startswith("B=")) if os.environ.get("VTOOL") else (lines[-1] if lines else r.stderr[-500:]))
