@@ -271,3 +271,45 @@ def test_argument_errors_and_degenerate_sizes(gpu_trackers):
     p.alpha = 2.5
     assert lib.mpcb_create(C.byref(h), C.byref(p), L._h, 0) == -1
     assert lib.mpcb_create(C.byref(h), C.byref(p), L._h, 99) != 0
+
+
+def test_repeated_host_calls_replay_fresh_data(gpu_trackers, port_tables):
+    """mpcb_solve_batch_host captures a CUDA graph on the second call with the same buffers and replays it afterwards:
+    the replays must read the buffers' CURRENT contents (both the chunked large-batch path, which copies straight
+    from / to the caller's page-locked arrays, and the packed small-batch path), pageable buffers must keep working
+    (no graph), and the answers must equal those of a fresh handle."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from oracle import tracker_port as P
+    L, _ = gpu_trackers[3]
+    x0, obs, n = P.monte_carlo_problems(port_tables[3], 3 * 6000)
+    for B in (6000, 700):                                    # chunked path / packed path
+        T = M.BatchedTracker(L)
+        fresh = M.BatchedTracker(L)
+        pin = {k: M.tracker.PinnedBuffer(a[:B].shape, a.dtype) for k, a in (("x0", x0), ("obs", obs), ("n", n))}
+        for rep in range(5):                                 # 0: direct, 1: capture + replay, 2..: replay
+            sl = slice((rep % 3) * B, (rep % 3) * B + B)
+            pin["x0"].array[...] = x0[sl]; pin["obs"].array[...] = obs[sl]; pin["n"].array[...] = n[sl]
+            r = {k: v.copy() for k, v in T.solve_batch_host(pin["x0"].array, pin["obs"].array, pin["n"].array).items()}
+            ref = fresh.solve_batch_host(x0[sl].copy(), obs[sl].copy(), n[sl].copy(), pinned_out=False)   # pageable: never a graph
+            assert np.array_equal(r["status"], ref["status"]), (B, rep)
+            assert np.array_equal(r["U"], ref["U"]), (B, rep)
+            assert np.array_equal(r["Xpred"], ref["Xpred"]), (B, rep)
+            assert np.array_equal(r["active"], ref["active"]), (B, rep)
+
+
+def test_first_pass_caps_do_not_change_answers(gpu_trackers, port_tables):
+    """The caps of the two-level policy in the thread-per-problem kernel only decide WHERE a problem is solved (first
+    pass or robust pass), not what comes out: flags equal, controls equal to 1e-6 across cap settings."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from oracle import tracker_port as P
+    L, T = gpu_trackers[3]
+    x0, obs, n = P.monte_carlo_problems(port_tables[3], 6000)
+    ref = {k: v.copy() for k, v in T.solve_batch_host(x0, obs, n).items()}
+    for kw in (dict(thread_max_rounds=4, thread_max_segments=2, thread_fail_rounds=0),
+               dict(thread_max_rounds=6, thread_max_segments=4, thread_fail_rounds=0),
+               dict(thread_max_rounds=5, thread_max_segments=1, thread_fail_rounds=5)):
+        r = M.BatchedTracker(L, **kw).solve_batch_host(x0, obs, n)
+        agree = r["status"] == ref["status"]
+        assert agree.mean() > 0.999, kw
+        ok = agree & (ref["status"] == 0)
+        assert np.abs(r["U"] - ref["U"])[ok].max() <= 1e-6, kw
