@@ -135,6 +135,19 @@ struct Problem {
 
 MPCB_HD double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 MPCB_HD double dmax(double a, double b) { return a > b ? a : b; }
+// rows by sidedness: 0 two-sided (box, lane), 1 lower bound only (speed), 2 upper bound only (obstacle); the absent side
+// is +-BIG, which no row value reaches, so its comparison is dropped at compile time
+template <int KIND> using RowKind = std::integral_constant<int, KIND>;
+template <int KIND> MPCB_HD double clipk(double v, double lo, double hi) {
+  if (KIND == 1) return v < lo ? lo : v;
+  if (KIND == 2) return v > hi ? hi : v;
+  return clipd(v, lo, hi);
+}
+template <int KIND> MPCB_HD bool outside(double v, double lo, double hi) {
+  if (KIND == 1) return v < lo;
+  if (KIND == 2) return v > hi;
+  return (v < lo) || (v > hi);
+}
 
 // ------------------------------------------------------------------------------------------------
 // Linearisation: rollout with forward sensitivities at pb.U; fills H, q, D, O, lane_c, lane_inrm.
@@ -303,8 +316,8 @@ MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const ST& st, const
   const double h = P.h;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
-    if (i & 1) f(i, x[i], st.blo[i >> 1], st.bhi[i >> 1]);
-    else f(i, x[i], P.umin[0], P.umax[0]);
+    if (i & 1) f(i, x[i], st.blo[i >> 1], st.bhi[i >> 1], RowKind<0>{});
+    else f(i, x[i], P.umin[0], P.umax[0], RowKind<0>{});
   }
 #pragma unroll
   for (int jj = 0; jj < 4; ++jj) {
@@ -314,9 +327,9 @@ MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const ST& st, const
       dj = fma(st.D[doff(jj) + c], x[c], dj);
       oj = fma(st.O[doff(jj) + c], x[c], oj);
     }
-    f(ROW_LANE + 2 * jj, dj, -P.sld - st.lane_c[2 * jj], P.sld - st.lane_c[2 * jj]);
+    f(ROW_LANE + 2 * jj, dj, -P.sld - st.lane_c[2 * jj], P.sld - st.lane_c[2 * jj], RowKind<0>{});
     f(ROW_LANE + 2 * jj + 1, fma(P.alpha_lane[2], oj, dj), -P.sld - st.lane_c[2 * jj + 1],
-      P.sld - st.lane_c[2 * jj + 1]);
+      P.sld - st.lane_c[2 * jj + 1], RowKind<0>{});
   }
   double cum = 0.0, Sj = 0.0;
 #pragma unroll
@@ -324,11 +337,11 @@ MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const ST& st, const
     // S_j = h sum_{m<j} (v_m - v0);  cum = v_j - v0
     if (j > 1) Sj = fma(h, cum, Sj);
     cum = fma(h, x[2 * (j - 1) + 1], cum);
-    f(ROW_V + j - 1, cum, st.lov[j - 1], BIG);
+    f(ROW_V + j - 1, cum, st.lov[j - 1], BIG, RowKind<1>{});
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (j > 1) f(row_r1(k, j), Sj, -BIG, st.hio[N_OBSROW * k + (j - 2)]);
-      f(row_r2(k, j), fma(P.tgap, cum, Sj), -BIG, st.hio[N_OBSROW * k + 4 + (j - 1)]);
+      if (j > 1) f(row_r1(k, j), Sj, -BIG, st.hio[N_OBSROW * k + (j - 2)], RowKind<2>{});
+      f(row_r2(k, j), fma(P.tgap, cum, Sj), -BIG, st.hio[N_OBSROW * k + 4 + (j - 1)], RowKind<2>{});
     }
   }
 }
@@ -510,9 +523,9 @@ MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const 
   // pass A: w_r = rho_r (2 clip(v_r) - v_r); the plain iteration folds "- alpha clip(v)" into v on the way
   {
     AtAcc<ST> acc(P, st, rhs);
-    for_rows(P, pb, st, pb.x, [&](int r, double, double lo, double hi) {
+    for_rows(P, pb, st, pb.x, [&](int r, double, double lo, double hi, auto kind) {
       const double v = st.v[r];
-      const double z = clipd(v, lo, hi);
+      const double z = clipk<decltype(kind)::value>(v, lo, hi);
       acc.add(r, st.rho[r] * fma(2.0, z, -v));
       if (!CHECK) st.v[r] = fma(-relax, z, v);
     });
@@ -520,7 +533,7 @@ MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const 
   }
   chol_solve(st, rhs, pb.x);
   if (!CHECK) {
-    for_rows(P, pb, st, pb.x, [&](int r, double zt, double, double) { st.v[r] = fma(relax, zt, st.v[r]); });
+    for_rows(P, pb, st, pb.x, [&](int r, double zt, double, double, auto) { st.v[r] = fma(relax, zt, st.v[r]); });
     return;
   }
   double o1[NV], o2[NV];
@@ -529,12 +542,13 @@ MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const 
   AtAcc<ST> acc1(P, st, o1), acc2(P, st, o2);
   double rp = 0.0, nd = 0.0, sup = 0.0, bad = 0.0;
   unsigned long long act = 0ull;
-  for_rows(P, pb, st, pb.x, [&](int r, double zt, double lo, double hi) {
+  for_rows(P, pb, st, pb.x, [&](int r, double zt, double lo, double hi, auto kind) {
+    constexpr int KIND = decltype(kind)::value;
     const double v = st.v[r];
     const double rho = st.rho[r];
-    const double z = clipd(v, lo, hi);
+    const double z = clipk<KIND>(v, lo, hi);
     const double vn = fma(relax, zt - z, v);
-    const double zn = clipd(vn, lo, hi);
+    const double zn = clipk<KIND>(vn, lo, hi);
     rp = dmax(rp, fabs(zt - zn));
     // dual residual of (x, y_new): A' rho ((2 - alpha) z + (alpha - 1) zt - zn)
     acc1.add(r, rho * (fma(2.0 - relax, z, (relax - 1.0) * zt) - zn));
@@ -546,7 +560,7 @@ MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const 
       acc2.add(r, dy);
     }
     // step-size policy
-    const bool a_now = (vn < lo) || (vn > hi);
+    const bool a_now = outside<KIND>(vn, lo, hi);
     const bool a_prev = (pb.act_prev >> r) & 1ull;
     double vnew = vn;
     if (TWO) {
@@ -682,7 +696,9 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
 #pragma unroll
     for (int i = 0; i < 6; ++i) pb.E.w[i] = 0x11111111u * (unsigned)pl.e_init;
     pb.act_prev = 0ull;
-    for_rows(P, pb, st, xx, [&](int r, double zt, double lo, double hi) { st.v[r] = clipd(zt, lo, hi); });
+    for_rows(P, pb, st, xx, [&](int r, double zt, double lo, double hi, auto kind) {
+      st.v[r] = clipk<decltype(kind)::value>(zt, lo, hi);
+    });
   };
   for (int round = 0; round < max_rounds; ++round) {
     if (MPCB_ALL(done)) break;
