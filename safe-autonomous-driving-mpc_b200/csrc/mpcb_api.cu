@@ -56,18 +56,40 @@ __device__ __forceinline__ bool finalize(const DevTable& T, const DevParams& P, 
   double X[NH + 1][5];
   double cost;
   rollout_values(T, P, pb.x0, pb.U, X, cost, pb.hint);
+  // constraint rows in the reference's order (constraint_rows of mpcb_device.cuh: 6 lane rows, one row per obstacle,
+  // the speed row, per step), evaluated at fixed positions -- both obstacle slots -- and then squeezed to the
+  // reference's bit positions with one shift per step instead of one per row
   double cmin = BIG;
   unsigned long long act = 0ull;
   int row = 0;
 #pragma unroll
   for (int j = 1; j <= NH; ++j) {
-    double rows[9];
-    const int nr = constraint_rows(P, X[j], j, pb.obs, pb.n_obs, rows);
-    for (int r = 0; r < nr; ++r) {
-      cmin = fmin(cmin, rows[r]);
-      if (rows[r] <= P.feas_tol) act |= (1ull << (row + r));
+    const double s = X[j][0], d = X[j][1], o = X[j][2], v = X[j][4];
+    unsigned m = 0u;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      const double val = d + P.alpha_lane[a] * o;
+      const double r0 = P.sld - val, r1 = val + P.sld;
+      cmin = fmin(cmin, fmin(r0, r1));
+      if (r0 <= P.feas_tol) m |= 1u << (2 * a);
+      if (r1 <= P.feas_tol) m |= 1u << (2 * a + 1);
     }
-    row += nr;
+    unsigned mo = 0u;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const double s_obs = pb.obs[k][0] + pb.obs[k][1] * (j * P.h);
+      const double safe = fmax(P.obs_safe, v * P.tgap);
+      const double r = (s_obs - s) - safe;
+      if (k < pb.n_obs) {
+        cmin = fmin(cmin, r);
+        if (r <= P.feas_tol) mo |= 1u << k;
+      }
+    }
+    cmin = fmin(cmin, v);
+    const unsigned mv = (v <= P.feas_tol) ? 1u : 0u;
+    m |= (mo << 6) | (mv << (6 + pb.n_obs));
+    act |= (unsigned long long)m << row;
+    row += 7 + pb.n_obs;
   }
 #pragma unroll
   for (int i = 0; i < NV; ++i)
