@@ -527,6 +527,11 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
     if (cudaMalloc(&c->d_lut, sizeof(int) * n) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
     if ((e = cudaMemcpy(c->d_lut, lut.data(), sizeof(int) * n, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
     c->dt.lut = c->d_lut; c->dt.lut_n = n; c->dt.lut_s0 = s0; c->dt.lut_scale = scale;
+    std::vector<double> sinv(K, 0.0);
+    for (int i = 1; i < K; ++i) sinv[i] = 1.0 / (t->s[i] - t->s[i - 1]);
+    if (cudaMalloc(&c->d_sinv, sizeof(double) * K) != cudaSuccess) return fail(cuda_fail(cudaGetLastError(), "cudaMalloc"));
+    if ((e = cudaMemcpy(c->d_sinv, sinv.data(), sizeof(double) * K, cudaMemcpyHostToDevice)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemcpy"));
+    c->dt.sinv = c->d_sinv;
   }
   for (int k = 0; k < 4; ++k) c->dt.last[k] = t->last_row[1 + k];
   *out = c;
@@ -540,6 +545,7 @@ int mpcb_destroy(mpcb_handle h) {
   if (h->d_y) cudaFree(h->d_y);
   if (h->d_u) cudaFree(h->d_u);
   if (h->d_lut) cudaFree(h->d_lut);
+  if (h->d_sinv) cudaFree(h->d_sinv);
   for (int k = 0; k < 2; ++k) {
     if (h->gslot[k].exec) cudaGraphExecDestroy(h->gslot[k].exec);
     if (h->gslot[k].graph) cudaGraphDestroy(h->gslot[k].graph);

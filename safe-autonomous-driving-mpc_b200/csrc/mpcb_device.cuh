@@ -50,6 +50,10 @@ struct DevTable {
   const int* lut;
   int lut_n;
   double lut_s0, lut_scale;
+  // optional 1 / (s[i] - s[i-1]) per segment (IEEE division done once when the table is built): the device lookups of
+  // the tracking path multiply by it instead of dividing three times per lookup (weights differ by at most one ulp
+  // from the reference's quotient form; the host build and the planner keep the divisions)
+  const double* sinv;
 };
 
 // Step-size policy of the ADMM machinery (mpcb_solver.cuh).
@@ -179,8 +183,13 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
     load_rows(i);
   }
   hint = i;
+#if defined(__CUDA_ARCH__)
+  const double inv = __ldg(T.sinv + i);
+  const double wl = (s - x_lo) * inv, wr = (x_hi - s) * inv;
+#else
   const double inv = 1.0 / (x_hi - x_lo);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
+#endif
 #pragma unroll
   for (int c = 0; c < 4; ++c) {
     val[c] = wl * yhi[c] + wr * ylo[c];
@@ -192,7 +201,12 @@ MPCB_HD void lookup_control(const DevTable& T, double s, double (&u)[2], int& hi
   if (s >= T.s_max) { u[0] = 0.0; u[1] = 0.0; return; }
   const int i = (hint > 0) ? seg_index_hint(T.s, T.Ku, s, hint) : (hint = seg_index_cold(T, T.Ku, s));
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
+#if defined(__CUDA_ARCH__)
+  const double inv = __ldg(T.sinv + i);
+  const double wl = (s - x_lo) * inv, wr = (x_hi - s) * inv;
+#else
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
+#endif
   const double ul0 = MPCB_LDG(T.u + 2 * (i - 1)), ul1 = MPCB_LDG(T.u + 2 * (i - 1) + 1);
   const double uh0 = MPCB_LDG(T.u + 2 * i), uh1 = MPCB_LDG(T.u + 2 * i + 1);
   u[0] = wl * uh0 + wr * ul0;

@@ -26,6 +26,7 @@ struct mpcb_ctx {
   double* d_y = nullptr;
   double* d_u = nullptr;
   int* d_lut = nullptr;
+  double* d_sinv = nullptr;
   // workspace for the host-buffer entry points
   void* ws = nullptr;
   size_t ws_bytes = 0;

@@ -25,7 +25,7 @@ static DevTable make_table(const double* s, const double* y, const double* u, in
                            const double* last4) {
   DevTable T;
   T.s = s; T.y = y; T.u = u; T.K = K; T.Ku = Ku; T.s_max = s_max;
-  T.lut = nullptr; T.lut_n = 0; T.lut_s0 = 0.0; T.lut_scale = 0.0;
+  T.lut = nullptr; T.lut_n = 0; T.lut_s0 = 0.0; T.lut_scale = 0.0; T.sinv = nullptr;
   for (int c = 0; c < 4; ++c) T.last[c] = last4[c];
   return T;
 }
