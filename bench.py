@@ -286,9 +286,10 @@ def run_ours(args):
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf,
                     # dram__bytes_read.sum + dram__bytes_write.sum of the two solve launches of one step, from the
-                    # ncu --set full capture of this workload (profiles/r01_v5_solve_kernels_ncu.txt); algorithmic
-                    # bytes are 416 B/solve = 27.3 MB: the excess is thread-local state written back from L2
-                    "traffic": 149.5e6 + 0.66e6,
+                    # ncu --set full capture of this workload (profiles/r01_v6_solve_kernels_ncu.txt; the r01 v5
+                    # capture of the same kernels read 149.5 MB: how much thread-local state L2 writes back varies from
+                    # run to run); algorithmic bytes are 416 B/solve = 27.3 MB
+                    "traffic": 72.8e6 + 0.65e6,
                     "note": "path is bound by the FP64 FMA pipe, not HBM or tensor cores (SURVEY 8d); peak = DFMA "
                             "loop measured in this run (mpcb_measure_fp64_peak); flops per SURVEY 8d formula with "
                             "the kernel's own per-problem round/iteration counts",
