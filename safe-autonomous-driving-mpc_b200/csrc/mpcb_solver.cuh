@@ -509,13 +509,15 @@ MPCB_HD void chol_solve(const ST& st, double (&r)[NV], double (&x)[NV]) {
   }
 }
 
-struct SegStats { double rp, rd, nd, atdy, sup, bad; };
+struct SegStats { double rp, rd, nd, atdy, sup, bad; };   // rp: 0 when every row's primal residual is within eps_p,
+                                                          // BIG otherwise (the exact maximum only in trace builds)
 
 // One ADMM iteration.
 //   CHECK = false: v += alpha (A x - clip(v)), nothing else.
 //   CHECK = true : additionally residuals, active set, step-size policy; CERT adds the infeasibility certificate.
 template <bool CHECK, bool CERT, bool TWO, class ST>
-MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const ST& st, SegStats& stt) {
+MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const ST& st, SegStats& stt,
+                       double eps_p = 0.0) {
   const double relax = pl.relax;
   double rhs[NV];
 #pragma unroll
@@ -549,7 +551,11 @@ MPCB_HD void admm_iter(const DevParams& P, const Policy& pl, Problem& pb, const 
     const double z = clipk<KIND>(v, lo, hi);
     const double vn = fma(relax, zt - z, v);
     const double zn = clipk<KIND>(vn, lo, hi);
+#ifdef MPCB_TRACE
     rp = dmax(rp, fabs(zt - zn));
+#else
+    if (!(fabs(zt - zn) <= eps_p)) rp = BIG;        // only "all rows within tolerance" is ever asked of rp
+#endif
     // dual residual of (x, y_new): A' rho ((2 - alpha) z + (alpha - 1) zt - zn)
     acc1.add(r, rho * (fma(2.0 - relax, z, (relax - 1.0) * zt) - zn));
     if (CERT) {
@@ -727,7 +733,7 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
         factor<FIRST_PASS>(P, pl, pb, st);
         SegStats s;
         for (int it = 0; it < pl.segment_iters - 1; ++it) admm_iter<false, false, FIRST_PASS>(P, pl, pb, st, s);
-        admm_iter<true, !FIRST_PASS, FIRST_PASS>(P, pl, pb, st, s);
+        admm_iter<true, !FIRST_PASS, FIRST_PASS>(P, pl, pb, st, s, eps_p);
         out.iters += pl.segment_iters;
 #ifdef MPCB_TRACE
         if (getenv("MPCB_TRACE")) {
