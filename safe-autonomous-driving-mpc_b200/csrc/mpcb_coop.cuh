@@ -1,16 +1,21 @@
 // mpcb_coop.cuh -- the same SQP / ADMM algorithm as mpcb_solver.cuh, executed by ONE WARP PER PROBLEM.
 //
 // Why a second execution shape: one thread per problem maximises throughput on a full batch but a single thread walks
-// ~1,400 instructions per ADMM iteration, so the few hard problems of the robust pass (and a B = 1 call) take as long
-// as their serial instruction chain.  Here the 41 rows of the QP are spread over the lanes (lane l owns rows l and
-// l + 32, as dense 10-vectors), the row work of an iteration is 2 rows per lane, A'w is a warp all-reduce of 10
-// partial sums, x = K^-1 rhs is one row of K^-1 per lane (lanes 0..9) followed by a broadcast, and the factorisation
-// is a lane-parallel Cholesky + 10 simultaneous substitutions: ~300 instructions per lane and iteration.
-// Scalar stages that run once per Gauss-Newton round (screen / warm start, linearisation, final evaluation) reuse the
-// thread-level code on lane 0 with a thread-private store placed in shared memory.
-//
-// Everything that decides control flow (residuals, certificate quantities, step) is all-reduced, so the lanes of a warp
-// take the same branches; warps are independent (no CTA barrier).
+// ~1,000 instructions per ADMM iteration, so the few hard problems of the robust pass (and a B = 1 call) take as long
+// as their serial instruction chain.  Here a warp runs alone on its scheduler and every dependent instruction costs
+// its full latency, so the code is arranged for short dependent chains:
+//   * the 41 rows of the QP are spread over the lanes (lane l owns rows l and l + 32 as dense 10-vectors, with their
+//     ADMM state in registers); without a second obstacle nobody has a second row and that work is skipped;
+//   * A'w: every lane publishes the weights of its rows, lane (i, part) adds up column i over a third of the rows,
+//     two shuffles combine the thirds; every lane then evaluates its row values as g_r . (A'w - q), g_r = K^-1 a_r
+//     precomputed per factorisation: one exchange and one broadcast per iteration; x is read off the box rows;
+//   * factorisation: K accumulated entry-per-lane in straight-line row blocks, Cholesky redundantly in registers;
+//   * linearisation by the whole warp (coop_linearise): sensitivity columns and H entries over the lanes, the six
+//     independent table lookups of a rollout on six lanes at once (likewise the five of the warm start);
+//   * residual / certificate tests as warp votes, so the lanes take the same branches; warps are independent (no CTA
+//     barrier) and pull their problems from a device counter (mpcb_api.cu).
+// The screen, the warm-start logic and the final evaluation reuse the thread-level code on lane 0 with a
+// thread-private store placed in shared memory.
 #pragma once
 #include "mpcb_solver.cuh"
 

@@ -18,9 +18,13 @@
 // exert no force, active rows are near-equalities: a primal-dual active-set iteration with augmented-Lagrangian
 // inner solves -- and hands whatever it cannot close to the robust pass, which walks a x10 ladder with hysteresis.
 //
-// Data placement: the per-row vectors (v, rho, obstacle bounds) and the lane sensitivities D, O live in a strided
-// store (shared memory on the GPU: element i of thread t at base[i * CTA + t], conflict free), the 10x10 factor,
-// H, q and the iterate in registers / local memory.
+// In the thread-per-problem kernel the first pass runs ONE segment per Gauss-Newton round and tolerates a few rounds
+// whose QP did not close (the ADMM state carries over: the active-set search continues on the next linearisation).
+//
+// Data placement: a compile-time mask (MPCB_STORE_MASK) says which per-thread arrays live in a strided store (shared
+// memory on the GPU: element i of thread t at base[i * CTA + t], conflict free) -- by default the per-row vectors v,
+// rho and the obstacle bounds -- and which stay thread-private (registers / local memory): D, O, the 10x10 factor, H,
+// q and the iterate.
 #pragma once
 #include <type_traits>
 
