@@ -71,7 +71,8 @@ typedef struct mpcb_params {
   int fast_max_segments;           /* default 4 */
   int fast_segment_iters;          /* default 2 */
   int coop_pass2;                  /* robust pass executed by one warp per problem (latency), default 1 */
-  int coop_max_batch;              /* batches up to this size run the first pass one warp per problem too, default 2048 */
+  int coop_max_batch;              /* batches up to this size run the first pass one warp per problem too, default 3072
+                                      (measured crossover with the thread-per-problem first pass: ~3,700 problems) */
   /* tighter caps of the two-level policy inside the thread-per-problem kernel, where the slowest problem of a CTA
    * holds up the other 127: what these caps cut off goes to the second pass (one warp per problem, nobody waits)
    * like everything else the first pass does not certify */

@@ -29,7 +29,7 @@ inline void default_params(mpcb_params* p) {
   p->fast_pass = 1;
   p->fast_rho_off = 1e-9; p->fast_rho_on = 1e6;
   p->fast_max_rounds = 6; p->fast_max_segments = 4; p->fast_segment_iters = 2;
-  p->coop_pass2 = 1; p->coop_max_batch = 2048;
+  p->coop_pass2 = 1; p->coop_max_batch = 3072;
   p->thread_max_rounds = 5; p->thread_max_segments = 1; p->thread_fail_rounds = 3;
 }
 

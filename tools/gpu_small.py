@@ -11,7 +11,7 @@ tab = P.RefTable.from_npz(f"{ROOT}/data/trajectory3.npz")
 x0, obs, n = P.monte_carlo_problems(tab, 65536)
 for cmb in (0, 1 << 30):
     T = M.BatchedTracker(L, coop_max_batch=cmb)
-    for B in (1, 32, 256, 1024, 2048, 4096, 8192):
+    for B in (1, 32, 256, 1024, 2048, 3072, 4096, 6144, 8192, 16384):
         dx, do, dn = (torch.from_numpy(a[:B]).cuda() for a in (x0, obs, n))
         out = T.solve_batch(dx, do, dn)
         torch.cuda.synchronize()
