@@ -165,6 +165,9 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
   int i = hint < 1 ? 1 : (hint > T.K - 1 ? T.K - 1 : hint);
   double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   double ylo[4], yhi[4];
+#if defined(__CUDA_ARCH__)
+  double inv = __ldg(T.sinv + i);             // speculative like the rest: no load waits for the hint check
+#endif
   auto load_rows = [&](int ii) {
 #if defined(__CUDA_ARCH__)
     const double2* yl = reinterpret_cast<const double2*>(T.y + 4 * (ii - 1));
@@ -180,11 +183,13 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
     i = seg_index_hint(T.s, T.K, s, hint);
     x_lo = MPCB_LDG(T.s + i - 1);
     x_hi = MPCB_LDG(T.s + i);
+#if defined(__CUDA_ARCH__)
+    inv = __ldg(T.sinv + i);
+#endif
     load_rows(i);
   }
   hint = i;
 #if defined(__CUDA_ARCH__)
-  const double inv = __ldg(T.sinv + i);
   const double wl = (s - x_lo) * inv, wr = (x_hi - s) * inv;
 #else
   const double inv = 1.0 / (x_hi - x_lo);
