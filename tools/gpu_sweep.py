@@ -13,10 +13,14 @@ x0, obs, n = P.monte_carlo_problems(tab, 65536)
 dx, do, dn = (torch.from_numpy(a).cuda() for a in (x0, obs, n))
 ref = None
 SWEEP = os.environ.get("SWEEP", "thread")
-grid = itertools.product((5, 6), (1, 2, 3), (3, 5)) if SWEEP == "thread" else itertools.product((4, 5, 6, 8, 10, 15), (0,), (1.5, 1.6, 1.7))
+grid = (itertools.product((5, 6), (1, 2, 3), (3, 5)) if SWEEP == "thread" else
+        itertools.product((1e4, 1e5, 1e6, 1e7, 1e8), (0,), (1e-9, 1e-6, 1e-4)) if SWEEP == "rho" else
+        itertools.product((4, 5, 6, 8, 10, 15), (0,), (1.5, 1.6, 1.7)))
 for rounds, segs, its in grid:
     if SWEEP == "thread":
         T = M.BatchedTracker(L, thread_max_rounds=rounds, thread_max_segments=1, fast_segment_iters=segs, thread_fail_rounds=its)
+    elif SWEEP == "rho":
+        T = M.BatchedTracker(L, fast_rho_on=rounds, fast_rho_off=its)
     else:
         T = M.BatchedTracker(L, segment_iters=rounds, max_segments=max(1, 120 // rounds), alpha=its)
     out = T.solve_batch(dx, do, dn)
