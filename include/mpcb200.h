@@ -135,6 +135,12 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
                           double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
                           double* cmin_out, unsigned long long* active_out);
 
+/* Closed-loop form of the host entry point: only what run_simulation consumes comes back (trajectory_tracking.py:260,
+ * :401-406) -- u0_out [B][2] = U*[0], status_out [B] (may be NULL), obj_out [B] (may be NULL): 20-28 bytes per solve over
+ * PCIe instead of 356.  Same solve, same flags as mpcb_solve_batch_host. */
+int mpcb_solve_batch_host_u0(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
+                             double* u0_out, int* status_out, double* obj_out);
+
 /* Evaluate the model functions at given controls (no optimisation).  DEVICE pointers, async on stream.
  *   U [B][10] -> Xpred_out [B][6][5] (predict), cost_out [B] (cost), cons_out [B][45] (constraints_wrapper rows,
  *   first 5*(7+n_obs[b]) valid, rest NaN), lin_out [B][150] (the solver's linearisation at U, packed: Gauss-Newton
@@ -159,6 +165,9 @@ int mpcb_last_kernel_ms(mpcb_handle h, float* ms);
 /* Device time of the two passes of the last solve (first: two-level pass incl. the list reset; second: robust pass over
  * the problems the first did not certify) and how many problems the second pass handled. */
 int mpcb_last_pass_ms(mpcb_handle h, float* first_ms, float* second_ms, int* n_second);
+/* Execution shape of the first pass of the last solve call: 0 one thread per problem (large batches), 1 one warp per
+ * problem (batches up to coop_max_batch).  Lets a test assert which kernel produced an answer. */
+int mpcb_last_first_pass_shape(mpcb_handle h);
 /* Number of kernels this library has launched on this handle since creation. */
 unsigned long long mpcb_launch_count(mpcb_handle h);
 
@@ -246,6 +255,14 @@ int mpcb_sim_history(mpcb_sim_handle s, int* n_recorded, double* hist_x, double*
  * within limits (+-0.1), 4 moving obstacle avoided (gap >= 1 m), 5 red light respected, 6 history covers the whole drive
  * (1 = passed).  metrics [B][4] HOST (may be NULL): max |d|, min gap to the car (1e30 if never present), final s, steps. */
 int mpcb_sim_check(mpcb_sim_handle s, int* verdict, double* metrics, void* cuda_stream);
+
+/* The same checks on histories the caller supplies (HOST arrays laid out like mpcb_sim_history returns them: hist_x
+ * [T][B][5] = state BEFORE each step, hist_u [T][B][2], hist_obs [T][B] (NaN: no car), hist_tl [T][B] (0 red, 1 green);
+ * x_final [B][5] = state after the last step, steps [B] = steps driven (<= T), scen [B]).  s_total = s_max of the
+ * trajectory.  Replaces trajectory_tracking_check (sanity_checks.py:79-184) for a batch of recorded drives. */
+int mpcb_check_histories(mpcb_handle h, int B, int T, double s_total, const mpcb_scenario* scen, const double* x_final,
+                         const int* steps, const double* hist_x, const double* hist_u, const double* hist_obs,
+                         const int* hist_tl, int* verdict, double* metrics);
 
 const char* mpcb_strerror(int code);
 const char* mpcb_last_cuda_error(void);

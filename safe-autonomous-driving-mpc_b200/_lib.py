@@ -78,6 +78,7 @@ SYMBOLS = {
     "mpcb_destroy": (C.c_int, [C.c_void_p]),
     "mpcb_solve_batch": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_void_p]),
     "mpcb_solve_batch_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 10),
+    "mpcb_solve_batch_host_u0": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 6),
     "mpcb_eval_batch": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_void_p]),
     "mpcb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_ulonglong]),
     "mpcb_host_free": (C.c_int, [C.c_void_p]),
@@ -87,6 +88,7 @@ SYMBOLS = {
     "mpcb_memcpy_d2h": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_ulonglong]),
     "mpcb_last_kernel_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "mpcb_last_pass_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_int)]),
+    "mpcb_last_first_pass_shape": (C.c_int, [C.c_void_p]),
     "mpcb_launch_count": (C.c_ulonglong, [C.c_void_p]),
     "mpcb_measure_fp64_peak": (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_float)]),
     "mpcb_planner_default_params": (C.c_int, [C.POINTER(PlannerParams)]),
@@ -99,6 +101,7 @@ SYMBOLS = {
     "mpcb_sim_alive": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "mpcb_sim_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpcb_sim_check": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "mpcb_check_histories": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_double, C.POINTER(Scenario)] + [C.c_void_p] * 8),
     "mpcb_sim_history": (C.c_int, [C.c_void_p, C.POINTER(C.c_int)] + [C.c_void_p] * 5 + [C.c_void_p]),
     "mpcb_strerror": (C.c_char_p, [C.c_int]),
     "mpcb_last_cuda_error": (C.c_char_p, []),

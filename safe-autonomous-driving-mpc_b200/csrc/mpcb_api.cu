@@ -31,16 +31,30 @@ using SolveStore = Store<(MPCB_STORE_MASK != 0 ? SOLVE_THREADS : 1), MPCB_STORE_
 constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::SHARED * SOLVE_THREADS;
 constexpr int EVAL_THREADS = 128;
 
+// Device pointers of one solve call (mpcb_solve_batch's arguments), handed to the kernels as one block.
+struct SolveIO {
+  const double* x0; const double* obs_sv; const int* n_obs;
+  double* U; double* Xpred; double* obj; int* status; int* iters; double* cmin; unsigned long long* active;
+  double* u0;           // optional compact [B][2]: the control a closed loop applies (trajectory_tracking.py:260)
+  const int* idx;       // optional work list: problems idx[0 .. *n_idx - 1] instead of 0 .. B-1
+  const int* n_idx;
+  int accumulate;       // second pass: add this pass's iteration counts to what the first pass recorded
+};
+
 // Final evaluation at U* (predict, cost, constraint rows in the reference's order), flags, outputs.  In the first pass a
 // problem that is not certified is appended to the work list of the next pass instead (fb_list == nullptr: the caller
 // goes on itself); its iteration counts are still recorded, the next pass adds its own.  Returns "written out".
 template <bool FIRST_PASS>
 __device__ __forceinline__ bool finalize(const DevTable& T, const DevParams& P, const Problem& pb, const SolveOut& so, int b,
-                                         bool accumulate, double* __restrict__ U_out, double* __restrict__ Xpred_out,
-                                         double* __restrict__ obj_out, int* __restrict__ status_out,
-                                         int* __restrict__ iters_out, double* __restrict__ cmin_out,
-                                         unsigned long long* __restrict__ active_out, int* __restrict__ fb_list,
+                                         bool accumulate, const SolveIO& io, int* __restrict__ fb_list,
                                          int* __restrict__ fb_count) {
+  double* __restrict__ U_out = io.U;
+  double* __restrict__ Xpred_out = io.Xpred;
+  double* __restrict__ obj_out = io.obj;
+  int* __restrict__ status_out = io.status;
+  int* __restrict__ iters_out = io.iters;
+  double* __restrict__ cmin_out = io.cmin;
+  unsigned long long* __restrict__ active_out = io.active;
   auto defer = [&]() {
     if (fb_list) fb_list[atomicAdd(fb_count, 1)] = b;
     if (iters_out) {
@@ -106,6 +120,7 @@ __device__ __forceinline__ bool finalize(const DevTable& T, const DevParams& P, 
 
 #pragma unroll
   for (int i = 0; i < NV; ++i) U_out[(size_t)b * NV + i] = pb.U[i];
+  if (io.u0) { io.u0[(size_t)b * 2] = pb.U[0]; io.u0[(size_t)b * 2 + 1] = pb.U[1]; }
   if (Xpred_out) {
 #pragma unroll
     for (int j = 0; j <= NH; ++j)
@@ -132,12 +147,9 @@ __device__ __forceinline__ bool finalize(const DevTable& T, const DevParams& P, 
 template <bool FIRST_PASS>
 __global__ void __launch_bounds__(SOLVE_THREADS, MPCB_SOLVE_CTAS)
 mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
-                  const int* __restrict__ idx, const int* __restrict__ n_idx,
-                  const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
-                  double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
-                  int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
-                  unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count) {
-  const int n_work = idx ? min(*n_idx, B) : B;
+                  const __grid_constant__ SolveIO io, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  const int* __restrict__ idx = io.idx;
+  const int n_work = idx ? min(*io.n_idx, B) : B;
   if ((int)(blockIdx.x * blockDim.x) >= n_work) return;          // CTA-uniform
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   const bool live = t < n_work;
@@ -145,10 +157,10 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
   Problem pb;
   if (live) {
 #pragma unroll
-    for (int c = 0; c < 5; ++c) pb.x0[c] = x0[(size_t)b * 5 + c];
+    for (int c = 0; c < 5; ++c) pb.x0[c] = io.x0[(size_t)b * 5 + c];
 #pragma unroll
-    for (int k = 0; k < 2; ++k) { pb.obs[k][0] = obs_sv[(size_t)b * 4 + 2 * k]; pb.obs[k][1] = obs_sv[(size_t)b * 4 + 2 * k + 1]; }
-    pb.n_obs = min(max(n_obs[b], 0), 2);
+    for (int k = 0; k < 2; ++k) { pb.obs[k][0] = io.obs_sv[(size_t)b * 4 + 2 * k]; pb.obs[k][1] = io.obs_sv[(size_t)b * 4 + 2 * k + 1]; }
+    pb.n_obs = min(max(io.n_obs[b], 0), 2);
   } else {
 #pragma unroll
     for (int c = 0; c < 5; ++c) pb.x0[c] = 0.0;
@@ -160,8 +172,7 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
   const SolveStore st(solve_smem + threadIdx.x, solve_local);
   SolveOut so = solve_one<FIRST_PASS>(T, P, pb, st, live);
   if (!live) return;
-  finalize<FIRST_PASS>(T, P, pb, so, b, idx != nullptr, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
-                       active_out, fb_list, fb_count);
+  finalize<FIRST_PASS>(T, P, pb, so, b, io.accumulate != 0, io, fb_list, fb_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -180,16 +191,13 @@ constexpr size_t COOP_SMEM = sizeof(WarpShared) * COOP_WARPS;
 template <bool FIRST_PASS>
 __global__ void __launch_bounds__(COOP_WARPS * 32, COOP_CTAS)
 mpcb_coop_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
-                 const int* __restrict__ idx, const int* __restrict__ n_idx,
-                 const double* __restrict__ x0, const double* __restrict__ obs_sv, const int* __restrict__ n_obs,
-                 double* __restrict__ U_out, double* __restrict__ Xpred_out, double* __restrict__ obj_out,
-                 int* __restrict__ status_out, int* __restrict__ iters_out, double* __restrict__ cmin_out,
-                 unsigned long long* __restrict__ active_out, int* __restrict__ fb_list, int* __restrict__ fb_count,
+                 const __grid_constant__ SolveIO io, int* __restrict__ fb_list, int* __restrict__ fb_count,
                  int* __restrict__ cursor) {
   extern __shared__ double coop_smem[];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   WarpShared& ws = reinterpret_cast<WarpShared*>(coop_smem)[wid];
-  const int n_work = idx ? min(*n_idx, B) : B;
+  const int* __restrict__ idx = io.idx;
+  const int n_work = idx ? min(*io.n_idx, B) : B;
   for (;;) {
     int t = 0;
     if (lane == 0) t = atomicAdd(cursor, 1);
@@ -197,14 +205,12 @@ mpcb_coop_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
     if (t >= n_work) break;
     const int b = idx ? idx[t] : t;
     __syncwarp();
-    if (lane < 5) ws.pb.x0[lane] = x0[(size_t)b * 5 + lane];
-    if (lane < 4) ws.pb.obs[lane >> 1][lane & 1] = obs_sv[(size_t)b * 4 + lane];
-    if (lane == 0) ws.pb.n_obs = min(max(n_obs[b], 0), 2);
+    if (lane < 5) ws.pb.x0[lane] = io.x0[(size_t)b * 5 + lane];
+    if (lane < 4) ws.pb.obs[lane >> 1][lane & 1] = io.obs_sv[(size_t)b * 4 + lane];
+    if (lane == 0) ws.pb.n_obs = min(max(io.n_obs[b], 0), 2);
     __syncwarp();
     const SolveOut so = coop_solve<FIRST_PASS>(T, P, ws, lane);
-    if (lane == 0)
-      finalize<FIRST_PASS>(T, P, ws.pb, so, b, idx != nullptr, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out,
-                           active_out, fb_list, fb_count);
+    if (lane == 0) finalize<FIRST_PASS>(T, P, ws.pb, so, b, io.accumulate != 0, io, fb_list, fb_count);
     __syncwarp();
   }
 }
@@ -328,7 +334,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 extern "C" {
 
-int mpcb_abi_version(void) { return 4; }
+int mpcb_abi_version(void) { return 5; }
 unsigned long long mpcb_sizeof_params(void) { return sizeof(mpcb_params); }
 unsigned long long mpcb_sizeof_planner_params(void) { return sizeof(mpcb_planner_params); }
 
@@ -581,65 +587,85 @@ static int ensure_fb(mpcb_handle h, int B) {
   return MPCB_OK;
 }
 
+// Timing events: inside a stream capture a plain cudaEventRecord does not become a node of the graph (the event would be
+// left "recorded in a capturing stream" and never fire on replay); cudaEventRecordExternal makes it an event-record node,
+// so mpcb_last_kernel_ms / mpcb_last_pass_ms keep working after a replayed call.
+static cudaError_t record_event(cudaEvent_t ev, cudaStream_t st) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaError_t e = cudaStreamIsCapturing(st, &cs);
+  if (e != cudaSuccess) return e;
+  return cudaEventRecordWithFlags(ev, st, cs == cudaStreamCaptureStatusActive ? cudaEventRecordExternal : cudaEventRecordDefault);
+}
+
+// Which execution shape a call of B_total problems uses (decided once per call, so that the parts of a chunked host
+// call keep the shape of the whole call and host and device entry points agree bit for bit).
+static bool call_uses_coop(mpcb_handle h, int B_total) { return h->params.fast_pass && B_total <= h->params.coop_max_batch; }
+
 // Enqueue the solve of B problems on `st`.  fb = [count, cursor, cursor, pad, idx[B]] (device ints) for the two-pass scheme.
 // timed: bracket the passes with the handle's events (single-stream callers only).
-static int launch_solve(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs, double* U_out,
-                        double* Xpred_out, double* obj_out, int* status_out, int* iters_out, double* cmin_out,
-                        unsigned long long* active_out, cudaStream_t st, int* fb, bool timed, bool whole_call = true) {
+// use_coop: first pass one warp per problem (call_uses_coop of the WHOLE call).  part: one part of a chunked host call
+// (second-pass grid sized for the expected leftovers, so that the parts do not queue whole grids of idle CTAs behind
+// each other's first passes); otherwise the second pass gets the full persistent grid -- a closed-loop step near a stop
+// line leaves a fifth of its problems to it, not the 1.4 % of the Monte-Carlo set.
+static int launch_solve(mpcb_handle h, int B, const SolveIO& io, cudaStream_t st, int* fb, bool timed, bool use_coop,
+                        bool part = false) {
   const int grid = (B + SOLVE_THREADS - 1) / SOLVE_THREADS;
-  if (timed) CK(cudaEventRecord(h->ev0, st));
+  h->last_shape = (h->params.fast_pass && use_coop) ? 1 : 0;
+  if (timed) CK(record_event(h->ev0, st));
   if (h->params.fast_pass) {
     int* fb_count = fb;
     int* fb_list = fb + FB_HDR;
     CK(cudaMemsetAsync(fb, 0, sizeof(int) * FB_HDR, st));
-    if (whole_call && B <= h->params.coop_max_batch) {   // (parts of a larger call keep the shape of the whole call)
+    if (use_coop) {
       // small batch: too few problems to fill the GPU with one thread each -> one warp per problem, for latency
       const int g1 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * COOP_CTAS);
-      mpcb_coop_kernel<true><<<g1, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs, U_out,
-                                                            Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
-                                                            fb_list, fb_count, fb + 1);
+      mpcb_coop_kernel<true><<<g1, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, io, fb_list, fb_count, fb + 1);
     } else {
-      mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
-                                                                      U_out, Xpred_out, obj_out, status_out, iters_out,
-                                                                      cmin_out, active_out, fb_list, fb_count);
+      mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, io, fb_list, fb_count);
     }
     CK(cudaGetLastError());
-    if (timed) CK(cudaEventRecord(h->ev_mid, st));
+    if (timed) CK(record_event(h->ev_mid, st));
     // second pass over whatever the first did not certify
+    SolveIO io2 = io;
+    io2.idx = fb_list;
+    io2.n_idx = fb_count;
+    io2.accumulate = 1;
     if (h->params.coop_pass2) {
       // one warp per problem: the leftovers are few and hard, what matters is their latency
-      // (after a thread-per-problem first pass a few per cent of the problems are left: a grid sized for that, so that
-      // the parts of a chunked host call do not queue whole grids of idle CTAs behind each other's first passes)
-      const bool small = whole_call && B <= h->params.coop_max_batch;
-      const int g2 = std::min(h->n_sm * COOP_CTAS, small ? (B + COOP_WARPS - 1) / COOP_WARPS : std::max(16, (B + 63) / 64));
-      mpcb_coop_kernel<false><<<g2, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv, n_obs, U_out,
-                                                             Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
-                                                             nullptr, nullptr, fb + 2);
+      const int full = std::min(h->n_sm * COOP_CTAS, (B + COOP_WARPS - 1) / COOP_WARPS);
+      const int g2 = (part && !use_coop) ? std::min(full, std::max(16, (B + 63) / 64)) : full;
+      mpcb_coop_kernel<false><<<g2, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, io2, nullptr, nullptr, fb + 2);
     } else {
       // thread per problem; CTAs beyond the list length exit at once (one warp per CTA when the working set is
       // thread-local: the few leftover warps then never wait for each other)
       const int t2 = (MPCB_STORE_MASK == 0) ? 32 : SOLVE_THREADS;
-      mpcb_solve_kernel<false><<<(B + t2 - 1) / t2, t2, SOLVE_SMEM, st>>>(h->dt, h->dp, B, fb_list, fb_count, x0, obs_sv,
-                                                                         n_obs, U_out, Xpred_out, obj_out, status_out,
-                                                                         iters_out, cmin_out, active_out, nullptr, nullptr);
+      mpcb_solve_kernel<false><<<(B + t2 - 1) / t2, t2, SOLVE_SMEM, st>>>(h->dt, h->dp, B, io2, nullptr, nullptr);
     }
     CK(cudaGetLastError());
     h->launches += 2;
   } else {
-    if (timed) CK(cudaEventRecord(h->ev_mid, st));
-    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, nullptr, nullptr, x0, obs_sv, n_obs,
-                                                                     U_out, Xpred_out, obj_out, status_out, iters_out,
-                                                                     cmin_out, active_out, nullptr, nullptr);
+    if (timed) CK(record_event(h->ev_mid, st));
+    mpcb_solve_kernel<false><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, io, nullptr, nullptr);
     CK(cudaGetLastError());
     h->launches++;
   }
   if (timed) {
-    CK(cudaEventRecord(h->ev1, st));
+    CK(record_event(h->ev1, st));
     h->timed = true;
     h->pass_timed = true;
     h->fb_last = fb;
   }
   return MPCB_OK;
+}
+
+static SolveIO make_io(const double* x0, const double* obs_sv, const int* n_obs, double* U_out, double* Xpred_out,
+                       double* obj_out, int* status_out, int* iters_out, double* cmin_out, unsigned long long* active_out,
+                       double* u0_out = nullptr) {
+  SolveIO io;
+  io.x0 = x0; io.obs_sv = obs_sv; io.n_obs = n_obs; io.U = U_out; io.Xpred = Xpred_out; io.obj = obj_out;
+  io.status = status_out; io.iters = iters_out; io.cmin = cmin_out; io.active = active_out; io.u0 = u0_out;
+  io.idx = nullptr; io.n_idx = nullptr; io.accumulate = 0;
+  return io;
 }
 
 int mpcb_solve_batch(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs, double* U_out,
@@ -650,14 +676,26 @@ int mpcb_solve_batch(mpcb_handle h, int B, const double* x0, const double* obs_s
   CK(cudaSetDevice(h->device));
   int rc = ensure_fb(h, B);
   if (rc != MPCB_OK) return rc;
-  return launch_solve(h, B, x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out,
-                      (cudaStream_t)cuda_stream, h->fb, true);
+  return launch_solve(h, B, make_io(x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out),
+                      (cudaStream_t)cuda_stream, h->fb, true, call_uses_coop(h, B));
+}
+
+// Solve the problems idx[0 .. *n_idx - 1] of a batch of B (both on the device; the closed loop's list of vehicles that
+// are still driving).  Outputs of the other problems are left untouched.
+int mpcb_solve_list_internal(mpcb_handle h, int B, const int* idx, const int* n_idx, const double* x0, const double* obs_sv,
+                             const int* n_obs, double* U_out, int* status_out, cudaStream_t st) {
+  int rc = ensure_fb(h, B);
+  if (rc != MPCB_OK) return rc;
+  SolveIO io = make_io(x0, obs_sv, n_obs, U_out, nullptr, nullptr, status_out, nullptr, nullptr, nullptr);
+  io.idx = idx;
+  io.n_idx = n_idx;
+  return launch_solve(h, B, io, st, h->fb, true, call_uses_coop(h, B));
 }
 
 static size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 // Lower edge of part c of a chunked host call, as a fraction of the batch (measured on B200, 65,536 problems: equal parts
-// 1.08 ms, 1/8 - 1/4 - 5/16 - 5/16 1.05 ms).  Development: MPCB_HOST_SPLIT="e1,e2,.." overrides the inner edges.
+// 1.08 ms, 1/8 - 1/4 - 5/16 - 5/16 1.05 ms).
 static double part_edge(int c) {
   static double edges[17];
   static bool init = false;
@@ -665,26 +703,28 @@ static double part_edge(int c) {
     for (int k = 0; k <= HOST_CHUNKS; ++k) edges[k] = (double)k / HOST_CHUNKS;
     if (HOST_CHUNKS == 4) { edges[1] = 0.125; edges[2] = 0.375; edges[3] = 0.6875; }   // small first part: its results start
                                                                                        // the device-to-host stream earlier
-    if (const char* e = getenv("MPCB_HOST_SPLIT")) {
+#ifdef MPCB_DEV
+    if (const char* e = getenv("MPCB_HOST_SPLIT")) {     // development builds only: "e1,e2,.." overrides the inner edges
       int k = 1;
       while (*e && k < HOST_CHUNKS) { edges[k++] = atof(e); while (*e && *e != ',') ++e; if (*e == ',') ++e; }
     }
+#endif
     init = true;
   }
   return edges[c];
 }
 
-// Host-buffer entry point.  Small batches (the reference's B = 1 call in particular) go through one packed pinned
+// Host-buffer entry points.  Small batches (the reference's B = 1 call in particular) go through one packed pinned
 // staging block: one H2D copy, the two launches, one D2H copy.  Large batches are cut into HOST_CHUNKS parts on as many
 // streams, each part copying straight from / to the caller's arrays, so that the H2D of one part, the kernels of
 // another and the D2H of a third overlap (PCIe is full duplex) and the latency tails of the parts' robust passes overlap
-// each other.
+// each other.  U_out may be NULL when u0_out is given (the closed-loop form: only U*[0] and the flags come back).
 static const int HOST_PACKED_MAX = 2048;
 
-int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
-                          double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
-                          double* cmin_out, unsigned long long* active_out) {
-  if (!h || B < 0 || (B > 0 && (!x0 || !obs_sv || !n_obs || !U_out))) return MPCB_ERR_INVALID;
+static int solve_host(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
+                      double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
+                      double* cmin_out, unsigned long long* active_out, double* u0_out) {
+  if (!h || B < 0 || (B > 0 && (!x0 || !obs_sv || !n_obs || (!U_out && !u0_out)))) return MPCB_ERR_INVALID;
   if (B == 0) return MPCB_OK;
   CK(cudaSetDevice(h->device));
   const size_t nb = (size_t)B;
@@ -692,7 +732,7 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
   const size_t o_x0 = 0, o_obs = o_x0 + al256(nb * 40), o_n = o_obs + al256(nb * 32), o_U = o_n + al256(nb * 4),
                o_X = o_U + al256(nb * 80), o_obj = o_X + al256(nb * 240), o_st = o_obj + al256(nb * 8),
                o_it = o_st + al256(nb * 4), o_cm = o_it + al256(nb * 8), o_ac = o_cm + al256(nb * 8),
-               total = o_ac + al256(nb * 8);
+               o_u0 = o_ac + al256(nb * 8), total = o_u0 + al256(nb * 16);
   if (total > h->ws_bytes) {
     if (h->ws) { cudaFree(h->ws); h->ws = nullptr; h->ws_bytes = 0; }
     if (cudaMalloc(&h->ws, total) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
@@ -708,37 +748,34 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
   int* dit = iters_out ? (int*)(w + o_it) : nullptr;
   double* dcm = cmin_out ? (double*)(w + o_cm) : nullptr;
   unsigned long long* dac = active_out ? (unsigned long long*)(w + o_ac) : nullptr;
+  double* du0 = u0_out ? (double*)(w + o_u0) : nullptr;
+  const bool use_coop = call_uses_coop(h, B);
 
   // ---- graph replay / capture bookkeeping --------------------------------------------------------------------
   const bool packed = B <= HOST_PACKED_MAX;
   if (packed && total > h->pin_bytes) {
     if (h->pin) { cudaFreeHost(h->pin); h->pin = nullptr; h->pin_bytes = 0; }
     size_t want = total;
-    { const size_t nmax = HOST_PACKED_MAX; want = std::max(want, (size_t)(al256(nmax * 40) + al256(nmax * 32) + 2 * al256(nmax * 4) + al256(nmax * 80) + al256(nmax * 240) + 4 * al256(nmax * 8))); }
+    { const size_t nmax = HOST_PACKED_MAX; want = std::max(want, (size_t)(al256(nmax * 40) + al256(nmax * 32) + 2 * al256(nmax * 4) + al256(nmax * 80) + al256(nmax * 240) + 4 * al256(nmax * 8) + al256(nmax * 16))); }
     if (cudaHostAlloc(&h->pin, want, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
     h->pin_bytes = want;
   }
   mpcb_ctx::GraphSlot& g = h->gslot[packed ? 0 : 1];
   // everything the enqueued work depends on: batch size, which outputs are wanted, the library's own buffers, and
   // (chunked path: the copies go straight from / to the caller's arrays) the caller's pointers
-  unsigned long long key[14] = {(unsigned long long)B, (unsigned long long)(size_t)h->ws, (unsigned long long)(size_t)h->fb,
-                                (unsigned long long)(size_t)h->pin,
-                                (unsigned long long)((Xpred_out != nullptr) | ((obj_out != nullptr) << 1) | ((status_out != nullptr) << 2) |
-                                                     ((iters_out != nullptr) << 3) | ((cmin_out != nullptr) << 4) | ((active_out != nullptr) << 5)),
-                                0, 0, 0, 0, 0, 0, 0, 0, 0};
-  if (!packed) {
-    const void* up[9] = {x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out};
-    for (int k = 0; k < 9; ++k) key[5 + k] = (unsigned long long)(size_t)up[k];
-    key[4] ^= (unsigned long long)(size_t)active_out << 8;
-  }
+  const void* up[11] = {x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out, u0_out};
+  unsigned long long key[16] = {(unsigned long long)B, (unsigned long long)(size_t)h->ws, (unsigned long long)(size_t)h->fb,
+                                (unsigned long long)(size_t)h->pin, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  for (int k = 3; k < 11; ++k) key[4] |= (unsigned long long)(up[k] != nullptr) << k;
+  if (!packed)
+    for (int k = 0; k < 11; ++k) key[5 + k] = (unsigned long long)(size_t)up[k];
   const bool hit = g.valid && memcmp(g.key, key, sizeof(key)) == 0;
   bool capture = false;
   if (!hit) {
     capture = g.have_last && memcmp(g.last, key, sizeof(key)) == 0;     // second call in a row with these buffers
     if (capture && !packed) {
       // a graph replays the copies asynchronously: only for page-locked caller buffers
-      const void* up[10] = {x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out};
-      for (int k = 0; k < 10 && capture; ++k) {
+      for (int k = 0; k < 11 && capture; ++k) {
         if (!up[k]) continue;
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, up[k]) != cudaSuccess || at.type != cudaMemoryTypeHost) { cudaGetLastError(); capture = false; }
@@ -749,15 +786,22 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
   }
   cudaStream_t s0 = h->xs[0];
 
-  // the device work of one call (the packed path keeps its per-pass timing events: in a graph they are event nodes)
+  // the device work of one call (the packed path keeps its per-pass timing events: captured, they become external
+  // event-record nodes, see record_event)
   auto enqueue = [&]() -> int {
     if (packed) {
       char* p = (char*)h->pin;
       CK(cudaMemcpyAsync(w, p, o_U, cudaMemcpyHostToDevice, s0));
-      int r = launch_solve(h, B, (double*)(w + o_x0), (double*)(w + o_obs), (int*)(w + o_n), dU, dX, dobj, dst, dit, dcm, dac,
-                           s0, h->fb, true);
+      int r = launch_solve(h, B, make_io((double*)(w + o_x0), (double*)(w + o_obs), (int*)(w + o_n), dU, dX, dobj, dst, dit, dcm,
+                                         dac, du0), s0, h->fb, true, use_coop);
       if (r != MPCB_OK) return r;
-      CK(cudaMemcpyAsync(p + o_U, w + o_U, total - o_U, cudaMemcpyDeviceToHost, s0));
+      // results: one copy of the whole output region, or -- closed-loop form -- the three small blocks only
+      if (U_out) CK(cudaMemcpyAsync(p + o_U, w + o_U, total - o_U, cudaMemcpyDeviceToHost, s0));
+      else {
+        CK(cudaMemcpyAsync(p + o_u0, w + o_u0, nb * 16, cudaMemcpyDeviceToHost, s0));
+        if (status_out) CK(cudaMemcpyAsync(p + o_st, w + o_st, nb * 4, cudaMemcpyDeviceToHost, s0));
+        if (obj_out) CK(cudaMemcpyAsync(p + o_obj, w + o_obj, nb * 8, cudaMemcpyDeviceToHost, s0));
+      }
       return MPCB_OK;
     }
     // chunked, one stream per part
@@ -770,12 +814,15 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
       CK(cudaMemcpyAsync(w + o_x0 + lo * 40, x0 + lo * 5, n * 40, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(w + o_obs + lo * 32, obs_sv + lo * 4, n * 32, cudaMemcpyHostToDevice, st));
       CK(cudaMemcpyAsync(w + o_n + lo * 4, n_obs + lo, n * 4, cudaMemcpyHostToDevice, st));
-      int r = launch_solve(h, (int)n, (double*)(w + o_x0) + lo * 5, (double*)(w + o_obs) + lo * 4, (int*)(w + o_n) + lo,
-                           dU + lo * 10, dX ? dX + lo * 30 : nullptr, dobj ? dobj + lo : nullptr, dst ? dst + lo : nullptr,
-                           dit ? dit + lo * 2 : nullptr, dcm ? dcm + lo : nullptr, dac ? dac + lo : nullptr, st,
-                           h->fb + lo + FB_HDR * c, false, false);
+      int r = launch_solve(h, (int)n,
+                           make_io((double*)(w + o_x0) + lo * 5, (double*)(w + o_obs) + lo * 4, (int*)(w + o_n) + lo, dU + lo * 10,
+                                   dX ? dX + lo * 30 : nullptr, dobj ? dobj + lo : nullptr, dst ? dst + lo : nullptr,
+                                   dit ? dit + lo * 2 : nullptr, dcm ? dcm + lo : nullptr, dac ? dac + lo : nullptr,
+                                   du0 ? du0 + lo * 2 : nullptr),
+                           st, h->fb + lo + FB_HDR * c, false, use_coop, true);
       if (r != MPCB_OK) return r;
-      CK(cudaMemcpyAsync(U_out + lo * 10, dU + lo * 10, n * 80, cudaMemcpyDeviceToHost, st));
+      if (U_out) CK(cudaMemcpyAsync(U_out + lo * 10, dU + lo * 10, n * 80, cudaMemcpyDeviceToHost, st));
+      if (u0_out) CK(cudaMemcpyAsync(u0_out + lo * 2, du0 + lo * 2, n * 16, cudaMemcpyDeviceToHost, st));
       if (Xpred_out) CK(cudaMemcpyAsync(Xpred_out + lo * 30, dX + lo * 30, n * 240, cudaMemcpyDeviceToHost, st));
       if (obj_out) CK(cudaMemcpyAsync(obj_out + lo, dobj + lo, n * 8, cudaMemcpyDeviceToHost, st));
       if (status_out) CK(cudaMemcpyAsync(status_out + lo, dst + lo, n * 4, cudaMemcpyDeviceToHost, st));
@@ -821,7 +868,7 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
     if (!packed) CK(cudaEventRecord(h->ev1, s0));
     h->launches += g.launches;
     h->timed = true;           // mpcb_last_kernel_ms: chunked path = device span of the whole call (copies included)
-    h->pass_timed = packed;
+    h->pass_timed = packed;    // packed path: the graph's own event-record nodes (ev0, ev_mid, ev1) fire on every replay
     h->fb_last = h->fb;
   } else {
     if (!packed) CK(cudaEventRecord(h->ev0, s0));
@@ -836,7 +883,8 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
   CK(cudaStreamSynchronize(s0));
   if (packed) {
     char* p = (char*)h->pin;
-    memcpy(U_out, p + o_U, nb * 80);
+    if (U_out) memcpy(U_out, p + o_U, nb * 80);
+    if (u0_out) memcpy(u0_out, p + o_u0, nb * 16);
     if (Xpred_out) memcpy(Xpred_out, p + o_X, nb * 240);
     if (obj_out) memcpy(obj_out, p + o_obj, nb * 8);
     if (status_out) memcpy(status_out, p + o_st, nb * 4);
@@ -845,6 +893,19 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
     if (active_out) memcpy(active_out, p + o_ac, nb * 8);
   }
   return MPCB_OK;
+}
+
+int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
+                          double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
+                          double* cmin_out, unsigned long long* active_out) {
+  if (B > 0 && !U_out) return MPCB_ERR_INVALID;
+  return solve_host(h, B, x0, obs_sv, n_obs, U_out, Xpred_out, obj_out, status_out, iters_out, cmin_out, active_out, nullptr);
+}
+
+int mpcb_solve_batch_host_u0(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
+                             double* u0_out, int* status_out, double* obj_out) {
+  if (B > 0 && !u0_out) return MPCB_ERR_INVALID;
+  return solve_host(h, B, x0, obs_sv, n_obs, nullptr, nullptr, obj_out, status_out, nullptr, nullptr, nullptr, u0_out);
 }
 
 int mpcb_eval_batch(mpcb_handle h, int B, const double* x0, const double* U, const double* obs_sv, const int* n_obs,
@@ -931,6 +992,7 @@ int mpcb_debug_coop_profile(unsigned long long* sum8, unsigned long long* max8, 
 #endif
 
 unsigned long long mpcb_launch_count(mpcb_handle h) { return h ? h->launches : 0ull; }
+int mpcb_last_first_pass_shape(mpcb_handle h) { return h ? h->last_shape : MPCB_ERR_INVALID; }
 
 int mpcb_measure_fp64_peak(mpcb_handle h, double* tflops, float* ms_out) {
   if (!h || !tflops) return MPCB_ERR_INVALID;

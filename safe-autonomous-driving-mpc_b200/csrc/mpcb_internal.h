@@ -41,15 +41,21 @@ struct mpcb_ctx {
   int* fb_last = nullptr;          // list used by the last timed solve
   bool timed = false;
   bool pass_timed = false;
+  int last_shape = 0;              // first pass of the last solve: 0 thread per problem, 1 warp per problem
   unsigned long long launches = 0;
   // CUDA graphs of the host-buffer entry point: the second call with the same batch size and the same buffers is
   // captured, later ones are one cudaGraphLaunch instead of ~50 enqueue calls.  [0] packed small-batch path, [1] chunked
   struct GraphSlot {
     bool valid = false, have_last = false;
-    unsigned long long key[14] = {0}, last[14] = {0};
+    unsigned long long key[16] = {0}, last[16] = {0};
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     unsigned long long launches = 0;
   } gslot[2];
   cudaEvent_t ev_fork = nullptr;
 };
+
+// Solve the problems idx[0 .. *n_idx - 1] (device list) of a batch of B on stream st; used by the device closed loop.
+extern "C" int mpcb_solve_list_internal(mpcb_handle h, int B, const int* idx, const int* n_idx, const double* x0,
+                                        const double* obs_sv, const int* n_obs, double* U_out, int* status_out,
+                                        cudaStream_t st);

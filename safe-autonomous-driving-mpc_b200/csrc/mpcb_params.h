@@ -86,7 +86,7 @@ inline int derive_params(const mpcb_params& p, DevParams& d) {
   d.qp_forcing = 1e-3; d.qp_eps_loose = 1e-4;
   d.max_fail_rounds = 2;
   d.fast_fail_rounds = p.thread_fail_rounds < 0 ? 0 : p.thread_fail_rounds;
-#ifndef __CUDACC__
+#if defined(MPCB_DEV) && !defined(__CUDACC__)   // development / host test builds only; the product reads no environment
   if (getenv("MPCB_FORCING")) d.qp_forcing = atof(getenv("MPCB_FORCING"));
   if (getenv("MPCB_MAXFAIL")) d.max_fail_rounds = atoi(getenv("MPCB_MAXFAIL"));
   if (getenv("MPCB_FASTFAIL")) d.fast_fail_rounds = atoi(getenv("MPCB_FASTFAIL"));

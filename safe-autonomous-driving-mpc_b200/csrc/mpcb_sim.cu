@@ -32,11 +32,24 @@ __global__ void __launch_bounds__(128)
 mpcb_fsm_kernel(int B, double dt, double s_stop, const double* __restrict__ x, const DevScenario* __restrict__ scen,
                 double* __restrict__ fsm_f, int* __restrict__ fsm_i, int* __restrict__ alive,
                 double* __restrict__ obs_sv, int* __restrict__ n_obs, int rec_t, double* __restrict__ hist_obs,
-                int* __restrict__ hist_tl) {
+                int* __restrict__ hist_tl, int* __restrict__ alive_idx, int* __restrict__ alive_cnt,
+                int* __restrict__ next_cnt) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= B) return;
-  const double s = x[(size_t)b * 5], v = x[(size_t)b * 5 + 4];
-  const int live = (s <= s_stop) ? 1 : 0;                    // loop condition (:395), evaluated before the step
+  if (b == 0) *next_cnt = 0;                                 // the other counter of the pair: next step's list length
+  const bool in = b < B;
+  const double s = in ? x[(size_t)b * 5] : 0.0, v = in ? x[(size_t)b * 5 + 4] : 0.0;
+  const int live = (in && s <= s_stop) ? 1 : 0;              // loop condition (:395), evaluated before the step
+  // list of the vehicles still driving: the solve of this step runs over the list, not over all B (one atomic per warp;
+  // the order of the list does not matter, every problem is solved on its own and written to its own slot)
+  {
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31;
+    int base = 0;
+    if (lane == 0 && m) base = atomicAdd(alive_cnt, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (live) alive_idx[base + __popc(m & ((1u << lane) - 1u))] = b;
+  }
+  if (!in) return;
   alive[b] = live;
   int n = 0;
   double o[4] = {0.0, 0.0, 0.0, 0.0};
@@ -177,6 +190,9 @@ struct mpcb_sim {
   double *x = nullptr, *fsm_f = nullptr, *obs_sv = nullptr, *U = nullptr;
   int *fsm_i = nullptr, *alive = nullptr, *n_obs = nullptr, *status = nullptr, *steps = nullptr, *n_unsolved = nullptr,
       *count = nullptr;
+  int *alive_idx = nullptr, *alive_cnt = nullptr;   // list of the vehicles still driving; its length, double-buffered
+  int* d_verdict = nullptr;                         // outputs of mpcb_sim_check (allocated with the histories)
+  double* d_metrics = nullptr;
   double *hist_x = nullptr, *hist_u = nullptr, *hist_obs = nullptr;
   int *hist_status = nullptr, *hist_tl = nullptr;
 };
@@ -201,7 +217,8 @@ int mpcb_sim_destroy(mpcb_sim_handle s) {
   if (!s) return MPCB_ERR_INVALID;
   cudaSetDevice(s->h->device);
   void* ptrs[] = {s->scen, s->x, s->fsm_f, s->obs_sv, s->U, s->fsm_i, s->alive, s->n_obs, s->status, s->steps,
-                  s->n_unsolved, s->count, s->hist_x, s->hist_u, s->hist_obs, s->hist_status, s->hist_tl};
+                  s->n_unsolved, s->count, s->hist_x, s->hist_u, s->hist_obs, s->hist_status, s->hist_tl, s->alive_idx,
+                  s->alive_cnt, s->d_verdict, s->d_metrics};
   for (void* p : ptrs) if (p) cudaFree(p);
   delete s;
   return MPCB_OK;
@@ -224,7 +241,9 @@ int mpcb_sim_create(mpcb_sim_handle* out, mpcb_handle h, int B, const mpcb_scena
   SIM_ALLOC(s->x, nb * 40); SIM_ALLOC(s->fsm_f, nb * 16); SIM_ALLOC(s->obs_sv, nb * 32); SIM_ALLOC(s->U, nb * 80);
   SIM_ALLOC(s->fsm_i, nb * 4); SIM_ALLOC(s->alive, nb * 4); SIM_ALLOC(s->n_obs, nb * 4); SIM_ALLOC(s->status, nb * 4);
   SIM_ALLOC(s->steps, nb * 4); SIM_ALLOC(s->n_unsolved, nb * 4); SIM_ALLOC(s->count, 4);
+  SIM_ALLOC(s->alive_idx, nb * 4); SIM_ALLOC(s->alive_cnt, 8);
   if (history_steps > 0) {
+    SIM_ALLOC(s->d_verdict, nb * 4); SIM_ALLOC(s->d_metrics, nb * 32);
     const size_t nt = (size_t)history_steps * nb;
     SIM_ALLOC(s->hist_x, nt * 40); SIM_ALLOC(s->hist_u, nt * 16); SIM_ALLOC(s->hist_obs, nt * 8);
     SIM_ALLOC(s->hist_status, nt * 4); SIM_ALLOC(s->hist_tl, nt * 4);
@@ -248,6 +267,9 @@ int mpcb_sim_create(mpcb_sim_handle* out, mpcb_handle h, int B, const mpcb_scena
   if ((e = cudaMemset(s->fsm_i, 0, nb * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
   if ((e = cudaMemset(s->steps, 0, nb * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
   if ((e = cudaMemset(s->n_unsolved, 0, nb * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
+  if ((e = cudaMemset(s->alive_cnt, 0, 8)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
+  if ((e = cudaMemset(s->status, 0, nb * 4)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
+  if ((e = cudaMemset(s->U, 0, nb * 80)) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset"));
   *out = s;
   return MPCB_OK;
 }
@@ -259,11 +281,13 @@ int mpcb_sim_step(mpcb_sim_handle s, int n_steps, void* cuda_stream) {
   const int grid = (s->B + 127) / 128;
   for (int k = 0; k < n_steps; ++k) {
     const int rec = (s->t < s->cap) ? s->t : -1;
+    int* cnt = s->alive_cnt + (s->t & 1);
     mpcb_fsm_kernel<<<grid, 128, 0, st>>>(s->B, s->dt, s->s_stop, s->x, s->scen, s->fsm_f, s->fsm_i, s->alive, s->obs_sv,
-                                          s->n_obs, rec, s->hist_obs, s->hist_tl);
+                                          s->n_obs, rec, s->hist_obs, s->hist_tl, s->alive_idx, cnt,
+                                          s->alive_cnt + ((s->t + 1) & 1));
     CK(cudaGetLastError());
-    int rc = mpcb_solve_batch(s->h, s->B, s->x, s->obs_sv, s->n_obs, s->U, nullptr, nullptr, s->status, nullptr, nullptr,
-                              nullptr, st);
+    // the solve runs over the list of vehicles still driving (arrived vehicles are frozen and cost nothing)
+    int rc = mpcb_solve_list_internal(s->h, s->B, s->alive_idx, cnt, s->x, s->obs_sv, s->n_obs, s->U, s->status, st);
     if (rc != MPCB_OK) return rc;
     mpcb_plant_kernel<<<grid, 128, 0, st>>>(s->h->dt, s->B, s->dt, s->x, s->U, s->status, s->alive, s->steps,
                                             s->n_unsolved, rec, s->hist_x, s->hist_u, s->hist_status);
@@ -303,22 +327,63 @@ int mpcb_sim_check(mpcb_sim_handle s, int* verdict, double* metrics, void* cuda_
   CK(cudaSetDevice(s->h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const size_t nb = (size_t)s->B;
-  int* d_v = nullptr;
-  double* d_m = nullptr;
-  CK(cudaMalloc((void**)&d_v, nb * 4));
-  if (cudaMalloc((void**)&d_m, nb * 32) != cudaSuccess) { cudaFree(d_v); cudaGetLastError(); return MPCB_ERR_NOMEM; }
   const mpcb_params& p = s->h->params;
   const int nt = s->t < s->cap ? s->t : s->cap;
   mpcb_sim_check_kernel<<<(s->B + 127) / 128, 128, 0, st>>>(s->B, nt, s->h->dt.s_max, p.u_min[0], p.u_max[0], p.u_min[1],
                                                            p.u_max[1], s->x, s->steps, s->scen, s->hist_x, s->hist_u,
-                                                           s->hist_obs, s->hist_tl, d_v, d_m);
-  cudaError_t e = cudaGetLastError();
-  if (e == cudaSuccess) e = cudaMemcpyAsync(verdict, d_v, nb * 4, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess && metrics) e = cudaMemcpyAsync(metrics, d_m, nb * 32, cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d_v); cudaFree(d_m);
-  if (e != cudaSuccess) return cuda_fail(e, "mpcb_sim_check");
+                                                           s->hist_obs, s->hist_tl, s->d_verdict, s->d_metrics);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(verdict, s->d_verdict, nb * 4, cudaMemcpyDeviceToHost, st));
+  if (metrics) CK(cudaMemcpyAsync(metrics, s->d_metrics, nb * 32, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
   s->h->launches += 1;
+  return MPCB_OK;
+}
+
+// The same checks on histories the CALLER supplies (host arrays, laid out like mpcb_sim_history returns them).  This is
+// the entry the parity tests use to compare the device checker with the reference's trajectory_tracking_check on
+// histories that FAIL an item (tests/golden/sanity_cases.npz).
+int mpcb_check_histories(mpcb_handle h, int B, int T, double s_total, const mpcb_scenario* scen, const double* x_final,
+                         const int* steps, const double* hist_x, const double* hist_u, const double* hist_obs,
+                         const int* hist_tl, int* verdict, double* metrics) {
+  if (!h || B < 1 || T < 1 || !scen || !x_final || !steps || !hist_x || !hist_u || !hist_obs || !hist_tl || !verdict)
+    return MPCB_ERR_INVALID;
+  CK(cudaSetDevice(h->device));
+  const size_t nb = (size_t)B, nt = (size_t)T * nb;
+  std::vector<DevScenario> hs(nb);
+  for (size_t b = 0; b < nb; ++b) {
+    const mpcb_scenario& c = scen[b];
+    hs[b] = DevScenario{c.obs_trigger_s, c.obs_start_s, c.obs_v, c.obs_end_s, c.tl_pos, c.tl_trigger_s,
+                        c.tl_stop_duration, c.dynamic_obstacle, c.traffic_light};
+  }
+  const size_t sz[8] = {nb * sizeof(DevScenario), nb * 40, nb * 4, nt * 40, nt * 16, nt * 8, nt * 4, ((nb * 4 + 255) & ~(size_t)255) + nb * 32};
+  const void* src[7] = {hs.data(), x_final, steps, hist_x, hist_u, hist_obs, hist_tl};
+  size_t off[9];
+  off[0] = 0;
+  for (int k = 0; k < 8; ++k) off[k + 1] = off[k] + ((sz[k] + 255) & ~(size_t)255);
+  char* d = nullptr;
+  if (cudaMalloc((void**)&d, off[8]) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
+  cudaStream_t st = h->stream;
+  cudaError_t e = cudaSuccess;
+  for (int k = 0; k < 7 && e == cudaSuccess; ++k) e = cudaMemcpyAsync(d + off[k], src[k], sz[k], cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) {
+    const mpcb_params& p = h->params;
+    int* d_v = (int*)(d + off[7]);
+    double* d_m = (double*)(d + off[7] + ((nb * 4 + 255) & ~(size_t)255));
+    // (the metrics block sits behind the verdicts inside the last region: re-derive its offset so both are aligned)
+    mpcb_sim_check_kernel<<<(B + 127) / 128, 128, 0, st>>>(B, T, s_total, p.u_min[0], p.u_max[0], p.u_min[1], p.u_max[1],
+                                                          (const double*)(d + off[1]), (const int*)(d + off[2]),
+                                                          (const DevScenario*)(d + off[0]), (const double*)(d + off[3]),
+                                                          (const double*)(d + off[4]), (const double*)(d + off[5]),
+                                                          (const int*)(d + off[6]), d_v, d_m);
+    e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(verdict, d_v, nb * 4, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess && metrics) e = cudaMemcpyAsync(metrics, d_m, nb * 32, cudaMemcpyDeviceToHost, st);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) return cuda_fail(e, "mpcb_check_histories");
+  h->launches += 1;
   return MPCB_OK;
 }
 

@@ -24,6 +24,38 @@ def make_scenario(which=2, **over):
     return s
 
 
+CHECKS = ("destination", "on_road", "steering", "acceleration", "obstacle", "light", "history_complete")
+
+
+def _verdict_dict(v, m):
+    out = {name: ((v >> k) & 1).astype(bool) for k, name in enumerate(CHECKS)}
+    out["passed"] = (v & 63) == 63
+    out.update(max_dev=m[:, 0], min_gap=m[:, 1], s_final=m[:, 2], steps=m[:, 3].astype(np.int64))
+    return out
+
+
+def check_histories(tracker, s_total, scenarios, x_final, steps, hist_x, hist_u, hist_obs, hist_tl):
+    """trajectory_tracking_check (sanity_checks.py:79-184) on the GPU for B recorded drives supplied by the caller:
+    hist_x [T,B,5] (state before each step), hist_u [T,B,2], hist_obs [T,B] (NaN: no car), hist_tl [T,B] (0 red,
+    1 green), x_final [B,5], steps [B].  Returns the same dict as ``BatchedSimulation.check``."""
+    lib = tracker._lib
+    hist_x = np.ascontiguousarray(hist_x, dtype=np.float64)
+    T, B = hist_x.shape[:2]
+    hist_u = np.ascontiguousarray(hist_u, dtype=np.float64).reshape(T, B, 2)
+    hist_obs = np.ascontiguousarray(hist_obs, dtype=np.float64).reshape(T, B)
+    hist_tl = np.ascontiguousarray(hist_tl, dtype=np.int32).reshape(T, B)
+    x_final = np.ascontiguousarray(x_final, dtype=np.float64).reshape(B, 5)
+    steps = np.ascontiguousarray(steps, dtype=np.int32).reshape(B)
+    scen = list(scenarios)
+    assert len(scen) == B
+    arr = (Scenario * B)(*scen)
+    v = np.empty(B, np.int32)
+    m = np.empty((B, 4))
+    check(lib.mpcb_check_histories(tracker._need(), B, T, float(s_total), arr, _dp(x_final), _dp(steps), _dp(hist_x),
+                                   _dp(hist_u), _dp(hist_obs), _dp(hist_tl), _dp(v), _dp(m)), "mpcb_check_histories")
+    return _verdict_dict(v, m)
+
+
 class BatchedSimulation:
     def __init__(self, tracker, scenarios, B=None, x_init=None, history_steps=0):
         """tracker: BatchedTracker; scenarios: one Scenario (shared) or a list of B; x_init: [B,5] or None for the
@@ -72,17 +104,14 @@ class BatchedSimulation:
         check(self._lib.mpcb_sim_history(self._h, C.byref(n), _dp(hx), _dp(hu), _dp(ho), _dp(hs), _dp(ht), None))
         return dict(x=hx, u=hu, obs_s=ho, status=hs, tl=ht)
 
-    CHECKS = ("destination", "on_road", "steering", "acceleration", "obstacle", "light", "history_complete")
+    CHECKS = CHECKS
 
     def check(self):
         """trajectory_tracking_check (sanity_checks.py:79-184) per vehicle: dict of bool arrays [B] plus metrics."""
         v = np.empty(self.B, np.int32)
         m = np.empty((self.B, 4))
         check(self._lib.mpcb_sim_check(self._h, _dp(v), _dp(m), None), "mpcb_sim_check")
-        out = {name: ((v >> k) & 1).astype(bool) for k, name in enumerate(self.CHECKS)}
-        out["passed"] = (v & 63) == 63
-        out.update(max_dev=m[:, 0], min_gap=m[:, 1], s_final=m[:, 2], steps=m[:, 3].astype(np.int64))
-        return out
+        return _verdict_dict(v, m)
 
     def run(self, max_steps=200000, check_every=64):
         """Drive until every vehicle has passed s_max - 1 (or max_steps).  Returns the number of steps enqueued."""

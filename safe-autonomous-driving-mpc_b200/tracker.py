@@ -211,6 +211,23 @@ class BatchedTracker:
                                               _dp(out["cmin"]), _dp(out["active"])), "mpcb_solve_batch_host")
         return out
 
+    def solve_batch_host_u0(self, x0, obs_sv, n_obs, want_obj=False, pinned_out=True):
+        """Closed-loop form: host arrays in, only ``U*[0]`` [B,2], ``status`` [B] (and ``obj`` [B]) out -- what
+        run_simulation consumes (trajectory_tracking.py:401-406) -- 20-28 bytes per solve over PCIe instead of 356."""
+        h = self._need()
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        B = x0.shape[0]
+        obs_sv = np.ascontiguousarray(obs_sv, dtype=np.float64).reshape(B, 2, 2)
+        n_obs = np.ascontiguousarray(n_obs, dtype=np.int32).reshape(B)
+        mk = (lambda k, s, d: self._pinned(k, s, d)) if pinned_out else (lambda k, s, d: np.empty(s, d))
+        out = dict(u0=mk("u0", (B, 2), np.float64), status=mk("st0", (B,), np.int32))
+        if want_obj:
+            out["obj"] = mk("obj0", (B,), np.float64)
+        check(self._lib.mpcb_solve_batch_host_u0(h, B, _dp(x0), _dp(obs_sv), _dp(n_obs), _dp(out["u0"]),
+                                                 _dp(out["status"]), _dp(out["obj"]) if want_obj else None),
+              "mpcb_solve_batch_host_u0")
+        return out
+
     def solve_batch(self, x0, obs_sv, n_obs, out=None, stream=None):
         """Device tensors in, device tensors out (torch used only for memory + stream hand-off).
         Asynchronous on ``stream`` (default: torch's current stream)."""
@@ -273,6 +290,10 @@ class BatchedTracker:
         a, b, n = C.c_float(), C.c_float(), C.c_int()
         check(self._lib.mpcb_last_pass_ms(self._need(), C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    def last_call_used_coop(self):
+        """True when the first pass of the last solve ran one warp per problem (small batches)."""
+        return self._lib.mpcb_last_first_pass_shape(self._need()) == 1
 
     def launch_count(self):
         return int(self._lib.mpcb_launch_count(self._need()))

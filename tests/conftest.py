@@ -39,3 +39,20 @@ def gpu_trackers():
         L = M.TrajectoryLoader(traj_path(i))
         out[i] = (L, M.BatchedTracker(L))
     return out
+
+
+# Execution shapes of the solve path.  "default": what a caller gets (batches up to coop_max_batch run one warp per
+# problem); "bulk": the thread-per-problem first pass that carries the benchmark, forced for every batch size, with the
+# warp-per-problem robust pass; "bulk_thread2": both passes thread-per-problem.
+VARIANTS = {"default": {}, "bulk": dict(coop_max_batch=0), "bulk_thread2": dict(coop_max_batch=0, coop_pass2=0)}
+
+
+@pytest.fixture(scope="session")
+def tracker_variants(gpu_trackers):
+    import safe_autonomous_driving_mpc_b200 as M
+    out = {"default": gpu_trackers}
+    for name, kw in VARIANTS.items():
+        if name == "default":
+            continue
+        out[name] = {i: (gpu_trackers[i][0], M.BatchedTracker(gpu_trackers[i][0], **kw)) for i in (1, 2, 3)}
+    return out

@@ -13,7 +13,7 @@ def build(force=False):
     deps = [src] + [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(ROOT, "include", "mpcb200.h")]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(d) <= os.path.getmtime(LIB) for d in deps):
         return LIB
-    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-DMPCB_HOST_SOLVER", "-DMPCB_TRACE", "-I", CSRC,
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-ffp-contract=off", "-DMPCB_HOST_SOLVER", "-DMPCB_TRACE", "-DMPCB_DEV", "-I", CSRC,
            "-I", os.path.join(ROOT, "include"), "-o", LIB, src]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:

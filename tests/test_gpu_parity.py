@@ -63,23 +63,52 @@ def _active_rows(c, n_obs, tol):
     return c[: 5 * (7 + n_obs)] <= tol
 
 
+def _other_local_optimum(tab, x0, obs, U_ours, J_ours, J_ref):
+    """The tracking NLP is nonconvex (bilinear dynamics, table looked up at the predicted s): in the tight bend of
+    trajectory3 (s ~ 720 m) a few problems have TWO local optima, and which one a solver reaches depends on its path
+    (SLSQP damps its steps with a line search, the Gauss-Newton SQP here takes full steps).  A returned point counts as
+    'another local optimum' only if the ORACLE's own SLSQP, started from it at tight tolerance, stays there (so it is
+    a stationary point of the reference formulation, not a solver artefact), it is feasible under the oracle's
+    constraints, and its objective is within 5 % of the reference's."""
+    from oracle import tracker_port as P
+    if P.constraint_values(tab, U_ours, x0, obs).min() < -1e-6:
+        return False
+    r = P.solve_converged(tab, x0, obs, U_start=U_ours)
+    return (np.max(np.abs(r.x - U_ours)) <= U_TOL and r.status in (0, 8) and abs(J_ours - J_ref) <= 0.05 * max(1.0, abs(J_ref)))
+
+
+@pytest.mark.parametrize("variant", ["default", "bulk", "bulk_thread2"])
 @pytest.mark.parametrize("name,i", SETS)
-def test_solve_against_converged_reference(name, i, gpu_trackers, port_tables):
-    """Solve-level parity against the reference formulation solved to convergence."""
+def test_solve_against_converged_reference(name, i, variant, tracker_variants, port_tables):
+    """Solve-level parity against the reference formulation solved to convergence, through every execution
+    shape: the warp-per-problem kernel a small batch gets by default, and -- forced with coop_max_batch=0 -- the
+    thread-per-problem first pass that carries the 65,536-problem benchmark (with either robust pass behind it)."""
     from oracle import tracker_port as P
     z = golden(name)
-    _, T = gpu_trackers[i]
+    _, T = tracker_variants[variant][i]
     s = T.solve_batch_host(z["x0"], z["obs_sv"], z["n_obs"])
     U = s["U"].reshape(-1, 10)
-    pin = z["pinned"]
+    pin = z["pinned"].copy()
     assert pin.sum() >= 0.8 * len(pin)
     # --- pinned problems: U, objective, flags, active set -------------------------------------
     err = np.abs(U - z["U_conv"]).max(axis=1)
+    # problems with two local optima (see _other_local_optimum): at most 0.1 % of a set, each verified with the oracle;
+    # they keep every other check below except the comparison with the reference's optimum
+    other = []
+    for b in np.where(pin & (err > U_TOL))[0]:
+        obs = [tuple(o) for o in z["obs_sv"][b, : z["n_obs"][b]]]
+        assert s["status"][b] == 0 and _other_local_optimum(port_tables[i], z["x0"][b], obs, U[b], s["obj"][b], z["J_conv"][b]), \
+            f"problem {b}: |dU| = {err[b]:.3e} and the returned point is not a stationary point of the reference NLP"
+        other.append(int(b))
+    assert len(other) <= max(1, len(pin) // 1000), other
+    pin[other] = False
     assert err[pin].max() <= U_TOL, f"max |dU| = {err[pin].max():.3e} at {np.argmax(np.where(pin, err, 0))}"
     jerr = np.abs(s["obj"] - z["J_conv"]) / np.maximum(np.abs(z["J_conv"]), 1.0)
     assert jerr[pin].max() <= J_RTOL
     assert np.all(s["status"][pin] == 0), "pinned (feasible, converged) problems must come back SOLVED"
     assert np.all(s["cmin"][pin] >= -1e-6)
+    if variant != "default":
+        assert T.last_pass_ms()[0] > 0.0 and not T.last_call_used_coop(), "the thread-per-problem first pass must have run"
     n_amb = 0
     for b in np.where(pin)[0]:
         no = int(z["n_obs"][b])
@@ -156,18 +185,23 @@ def test_edge_cases(gpu_trackers):
 
 
 def test_full_size_batch_properties(gpu_trackers, port_tables):
-    """BASELINE config 4 at full size (65,536 problems on trajectory3): size-independent properties.
+    """BASELINE config 4 at full size (65,536 problems on trajectory3): size-independent properties, judged with the
+    oracle's functions only (tests/kkt.py) -- nothing the device reports about itself is trusted except the controls.
     (a) shard/permutation invariance is bitwise (problems are independent, SURVEY 4.4-6);
-    (b) SOLVED problems satisfy every reference constraint and the bounds;
+    (b) every SOLVED problem satisfies every row of the reference's constraints_wrapper, evaluated by the oracle at the
+        returned controls, and the bounds; every INFEASIBLE flag comes with a violated oracle row;
     (c) u1_4 == 0 at every optimum (SURVEY A.1 known answer);
-    (d) first-order optimality of the reference cost on problems whose only active constraints are bounds;
-    (e) the objective returned equals the reference cost evaluated at the returned controls."""
-    from oracle import tracker_port as P, sqp_admm_model as A
+    (d) first-order optimality WITH multipliers: for every solved problem a non-negative least-squares fit of the
+        oracle's cost gradient on the gradients of its active rows and bounds leaves no residual;
+    (e) objective, cmin and the active-set bits returned equal the oracle's values at the returned controls."""
+    from oracle import tracker_port as P
+    import kkt
     tab = port_tables[3]
     _, T = gpu_trackers[3]
     B = 65536
     x0, obs, n = P.monte_carlo_problems(tab, B)
     full = {k: v.copy() for k, v in T.solve_batch_host(x0, obs, n).items()}
+    assert not T.last_call_used_coop()
     # (a) two shards, then a permutation
     h = B // 2
     for sl in (slice(0, h), slice(h, B)):
@@ -177,30 +211,32 @@ def test_full_size_batch_properties(gpu_trackers, port_tables):
     perm = np.random.default_rng(5).permutation(B)[:8192]
     part = T.solve_batch_host(x0[perm], obs[perm], n[perm])
     assert np.array_equal(part["U"], full["U"][perm]) and np.array_equal(part["status"], full["status"][perm])
-    # (b)
+    # (b) feasibility from the oracle's rows
+    U = full["U"].reshape(B, 10)
+    c, G, asm = kkt.reference_rows(tab, x0, U, obs, n)
+    cmin = np.nanmin(c, axis=1)
     ok = full["status"] == 0
     assert ok.mean() > 0.9
-    assert np.all(full["cmin"][ok] >= -1e-6)
-    U = full["U"].reshape(B, 10)
+    assert cmin[ok].min() >= -1e-6, f"a SOLVED problem violates a reference row by {cmin[ok].min():.3e}"
     assert np.all(U >= np.tile(P.U_MIN, 5) - 1e-12) and np.all(U <= np.tile(P.U_MAX, 5) + 1e-12)
-    # infeasible flags <-> violated constraints
     bad = full["status"] == 2
-    assert np.all(full["cmin"][bad] < -1e-6)
+    assert np.all(cmin[bad] < -1e-6), "an INFEASIBLE flag on a point that satisfies every reference row"
     assert np.all(full["status"] != 1), "no problem of the Monte-Carlo set should run out of iterations"
     # (c)
     assert np.max(np.abs(U[ok, 8])) < 1e-6
-    # (d) + (e)
-    asm = A.assemble(tab, x0, U)
+    # (e) what the device reports equals the oracle's evaluation at the same controls
     assert np.max(np.abs(asm["cost"] - full["obj"]) / np.maximum(1.0, np.abs(asm["cost"]))) < 1e-12
-    g = np.einsum("bk,bki->bi", 2.0 * A.W15 * asm["r"], asm["Jr"]) + U
-    rows_active = (full["active"] & np.uint64((1 << 45) - 1)) != 0
-    sel = ok & ~rows_active
-    lo = U - np.tile(P.U_MIN, 5) <= 1e-6
-    hi = np.tile(P.U_MAX, 5) - U <= 1e-6
-    free = ~(lo | hi)
-    assert sel.sum() > 1000
-    assert np.max(np.abs(g[sel][free[sel]])) < 1e-5
-    assert np.all(g[sel][lo[sel]] >= -1e-5) and np.all(g[sel][hi[sel]] <= 1e-5)
+    assert np.max(np.abs(cmin - full["cmin"]) / np.maximum(1.0, np.abs(cmin))) < 1e-10
+    bits = ((full["active"][:, None] >> np.arange(45, dtype=np.uint64)[None, :]) & np.uint64(1)).astype(bool)
+    valid = ~np.isnan(c)
+    clear_on = valid & (c <= 1e-6 - 1e-9)
+    clear_off = valid & (c > 1e-6 + 1e-9)
+    assert np.all(bits[clear_on]) and not np.any(bits[clear_off]) and not np.any(bits[~valid])
+    # (d) KKT with multipliers, all solved problems
+    g = kkt.cost_gradient(asm, U)
+    res, nact = kkt.kkt_residual(c[ok], G[ok], g[ok], U[ok])
+    assert (nact > 0).sum() > 500, "the set must contain problems that sit on constraints"
+    assert res.max() <= 1e-5, f"KKT residual {res.max():.3e} at solved problem {np.where(ok)[0][np.argmax(res)]}"
 
 
 def test_device_tensor_entry_point(gpu_trackers, port_tables):
@@ -229,7 +265,7 @@ def test_execution_shapes_agree(gpu_trackers, port_tables):
     L, T = gpu_trackers[3]
     x0, obs, n = P.monte_carlo_problems(port_tables[3], 6000)
     ref = {k: v.copy() for k, v in T.solve_batch_host(x0, obs, n).items()}
-    variants = dict(thread_pass2=dict(coop_pass2=0), robust_only=dict(fast_pass=0), no_small_coop=dict(coop_max_batch=0))
+    variants = dict(thread_pass2=dict(coop_pass2=0), robust_only=dict(fast_pass=0))
     for name, kw in variants.items():
         Tv = M.BatchedTracker(L, **kw)
         r = Tv.solve_batch_host(x0, obs, n)
@@ -237,8 +273,10 @@ def test_execution_shapes_agree(gpu_trackers, port_tables):
         assert agree.mean() > 0.999, name                     # borderline flags may flip between solver paths
         ok = agree & (ref["status"] == 0)
         assert np.abs(r["U"] - ref["U"])[ok].max() <= 1e-6, name
+    assert not T.last_call_used_coop()
     for nb in (700, 3000):                                      # B <= coop_max_batch: warp-per-problem first pass
         small = T.solve_batch_host(x0[:nb], obs[:nb], n[:nb])   # (700: packed staging path, 3000: chunked copies)
+        assert T.last_call_used_coop()
         same = small["status"] == ref["status"][:nb]
         assert same.mean() > 0.999
         ok = same & (small["status"] == 0)
@@ -314,3 +352,44 @@ def test_first_pass_caps_do_not_change_answers(gpu_trackers, port_tables):
         assert agree.mean() > 0.999, kw
         ok = agree & (ref["status"] == 0)
         assert np.abs(r["U"] - ref["U"])[ok].max() <= 1e-6, kw
+
+
+def test_timing_queries_after_graph_replay(gpu_trackers, port_tables):
+    """mpcb_last_kernel_ms / mpcb_last_pass_ms after a REPLAYED host call (the third identical call onwards runs as a
+    CUDA graph; its timing events are external event-record nodes of that graph) -- packed and chunked paths."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from oracle import tracker_port as P
+    L, _ = gpu_trackers[3]
+    x0, obs, n = P.monte_carlo_problems(port_tables[3], 6000)
+    for B in (1, 700, 6000):
+        T = M.BatchedTracker(L)
+        pin = {k: M.tracker.PinnedBuffer(a[:B].shape, a.dtype) for k, a in (("x0", x0), ("obs", obs), ("n", n))}
+        pin["x0"].array[...] = x0[:B]; pin["obs"].array[...] = obs[:B]; pin["n"].array[...] = n[:B]
+        for rep in range(5):
+            T.solve_batch_host(pin["x0"].array, pin["obs"].array, pin["n"].array)
+            ms = T.last_kernel_ms()
+            assert 0.0 < ms < 50.0, (B, rep, ms)
+            if B <= 2048:                                     # packed path keeps the per-pass split, replayed or not
+                a, b, k = T.last_pass_ms()
+                assert a > 0.0 and b >= 0.0 and 0 <= k <= B, (B, rep, a, b, k)
+    # the reference-shaped call: solve() three times, then the timing query (ADVICE r01)
+    T = M.BatchedTracker(L)
+    for _ in range(4):
+        T.solve(x0[0], [])
+    assert T.last_kernel_ms() > 0.0 and T.last_pass_ms()[0] > 0.0
+
+
+def test_closed_loop_form_of_the_host_entry(gpu_trackers, port_tables):
+    """mpcb_solve_batch_host_u0 returns exactly U*[0], status and objective of mpcb_solve_batch_host (same solve, 20-28
+    bytes per problem over PCIe), for the packed and the chunked path, replayed calls included."""
+    from oracle import tracker_port as P
+    _, T = gpu_trackers[3]
+    x0, obs, n = P.monte_carlo_problems(port_tables[3], 9000)
+    for B in (1, 900, 9000):
+        full = {k: v.copy() for k, v in T.solve_batch_host(x0[:B], obs[:B], n[:B]).items()}
+        for rep in range(4):
+            r = T.solve_batch_host_u0(x0[:B], obs[:B], n[:B], want_obj=True)
+            assert np.array_equal(r["u0"], full["U"][:, 0, :]), (B, rep)
+            assert np.array_equal(r["status"], full["status"]) and np.array_equal(r["obj"], full["obj"]), (B, rep)
+        r = T.solve_batch_host_u0(x0[:B], obs[:B], n[:B], pinned_out=False)
+        assert np.array_equal(r["u0"], full["U"][:, 0, :]) and "obj" not in r

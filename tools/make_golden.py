@@ -191,12 +191,12 @@ def make_solve_from_closed_loop(i, pool, per=72):
                 extra=dict(step_index=idx))
 
 
-def make_solve_mc(pool, n=256):
+def make_solve_mc(pool, n=2048):
     from oracle import tracker_port as P
     tab = P.RefTable.from_npz(os.path.join(ROOT, "data", "trajectory3.npz"))
     x0, obs, n_obs = P.monte_carlo_problems(tab, 65536)
     x0, obs, n_obs = x0[:n], obs[:n], n_obs[:n]
-    res = pool.map(_solve_one, [(3, x0[t].copy(), obs[t].copy(), int(n_obs[t])) for t in range(n)], chunksize=1)
+    res = pool.map(_solve_one, [(3, x0[t].copy(), obs[t].copy(), int(n_obs[t])) for t in range(n)], chunksize=4)
     _pack_solve(os.path.join(OUT, "solve_mc_traj3.npz"), 3, x0, obs, n_obs, res)
 
 
@@ -204,6 +204,7 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--procs", type=int, default=8)
     ap.add_argument("--only", default="all")
+    ap.add_argument("--mc-n", type=int, default=2048, help="Monte-Carlo problems with a converged answer (BASELINE.md 3)")
     a = ap.parse_args()
     os.makedirs(OUT, exist_ok=True)
     with mp.Pool(a.procs) as pool:
@@ -212,7 +213,7 @@ if __name__ == "__main__":
         if a.only in ("all", "closed_loop"):
             pool.map(make_closed_loop, [3, 2, 1])
         if a.only in ("all", "mc"):
-            make_solve_mc(pool)
+            make_solve_mc(pool, a.mc_n)
         if a.only in ("all", "solve"):
             for i in (1, 2, 3):
                 make_solve_from_closed_loop(i, pool)
