@@ -44,9 +44,9 @@ def test_device_loop_matches_host_driven_loop(i, gpu_trackers):
     c = sim.check()
     assert c["passed"][0] and c["history_complete"][0] and c["steps"][0] == k
     assert abs(c["max_dev"][0] - np.abs(np.vstack([h["x"][:k, 0], x[:1]])[:, 1]).max()) == 0.0
-    # same verdict data as the reference run (step count of the as-shipped reference within 1 %)
+    # same step count as the unmodified reference's own run (172 / 985 / 2294)
     z = golden(f"closed_loop_traj{i}")
-    assert abs(k - len(z["hist_u"])) <= max(2, int(0.01 * len(z["hist_u"])))
+    assert k == len(z["hist_u"])
 
 
 def test_many_vehicles_monte_carlo(gpu_trackers):
@@ -101,3 +101,55 @@ def test_many_vehicles_monte_carlo(gpu_trackers):
         for name, val in ref.items():
             assert bool(c[name][b]) == val, (b, name)
     assert c["passed"].all() and c["history_complete"].all()
+
+
+def test_device_checks_against_the_reference_function(gpu_trackers):
+    """mpcb_check_histories (the kernel behind BatchedSimulation.check) against the UNMODIFIED reference's
+    trajectory_tracking_check (sanity_checks.py:79-184) on recorded drives that pass and on variants that FAIL an item:
+    stopped short, |d| > 1.5, a control past its limit +- 0.1 (and exactly on it), the car within 1 m (and exactly 1 m,
+    and behind), a run red light, items switched off in the scenario, several at once.  Fixture:
+    tests/golden/sanity_cases.npz from tools/make_golden_sanity.py (verdict per item parsed from the reference's
+    output, overall verdict = its return value)."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from safe_autonomous_driving_mpc_b200 import simulation as S
+    z = golden("sanity_cases")
+    _, T = gpu_trackers[2]
+    names = [str(x) for x in z["item_names"]]
+    assert (~z["ref_passed"]).sum() >= 10 and z["ref_passed"].sum() >= 5
+    for s_total in np.unique(z["s_total"]):
+        sel = np.where(z["s_total"] == s_total)[0]
+        scen = [M.make_scenario(2, dynamic_obstacle=int(z["dynamic_obstacle"][b]), traffic_light=int(z["traffic_light"][b]),
+                                tl_pos=float(z["tl_pos"][b])) for b in sel]
+        c = S.check_histories(T, float(s_total), scen, z["x_final"][sel], z["steps"][sel], z["hist_x"][:, sel],
+                              z["hist_u"][:, sel], z["hist_obs"][:, sel], z["hist_tl"][:, sel])
+        for k, b in enumerate(sel):
+            for j, name in enumerate(names):
+                assert bool(c[name][k]) == bool(z["ref_items"][b, j]), (str(z["names"][b]), name)
+            assert bool(c["passed"][k]) == bool(z["ref_passed"][b]), str(z["names"][b])
+            assert c["steps"][k] == z["steps"][b] and c["history_complete"][k]
+
+
+def test_stop_line_inside_the_tight_bend_is_a_fixed_point(gpu_trackers):
+    """Known limitation (DESIGN.md 4, K-sim): a red light placed INSIDE the tight bend of trajectory3 (s ~ 720-728 m),
+    where the committed reference trajectory itself leaves the lane margin, makes the tracking MPC as formulated a
+    fixed point at standstill -- the optimum of the reference formulation is 'stay put'.  This test pins that behaviour
+    (the vehicle stops before the line, never runs the light, never leaves the road, never collides) instead of leaving
+    it undocumented; nothing on the three committed scenarios comes near this state."""
+    import safe_autonomous_driving_mpc_b200 as M
+    L, T = gpu_trackers[3]
+    scen = M.make_scenario(3, dynamic_obstacle=0, tl_pos=726.0, tl_stop_duration=6.0)
+    x_init = np.tile(L.get_state(600.0), (1, 1))
+    x_init[0, 4] = 6.0
+    sim = M.BatchedSimulation(T, scen, B=1, x_init=x_init, history_steps=1500)
+    sim.step(1500)
+    x, steps, unsolved = sim.state()
+    h = sim.history()
+    k = int(steps[0])
+    red = h["tl"][:k, 0] == 0
+    assert np.all(h["x"][:k, 0, 0][red] <= 726.0 + 1e-9), "ran the red light"
+    assert np.abs(h["x"][:k, 0, 1]).max() <= 1.5 and np.all(np.isfinite(x))
+    assert h["x"][:k, 0, 4].min() >= -0.25                    # no reversing beyond the reference's own creep
+    # it reaches the stop line region and comes to rest there
+    assert h["x"][:k, 0, 0].max() > 700.0
+    if x[0, 0] <= 726.0:                                      # stuck at the fixed point: at rest, same answer every step
+        assert abs(x[0, 4]) < 0.05 and np.abs(np.diff(h["x"][k - 50:k, 0, 0])).max() < 1e-3
