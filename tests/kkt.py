@@ -13,13 +13,18 @@ from oracle import sqp_admm_model as A
 from oracle import tracker_port as P
 
 
-def reference_rows(tab, x0, U, obs_sv, n_obs):
-    """c [B,45] (NaN beyond 5*(7+n_obs)) in the reference's row order, G [B,45,10] = dc/dU, asm (the rollout)."""
+def reference_rows(tab, x0, U, obs_sv, n_obs, with_kinks=False):
+    """c [B,45] (NaN beyond 5*(7+n_obs)) in the reference's row order, G [B,45,10] = dc/dU, asm (the rollout).
+    The obstacle row gap - max(5, 1.5 v) (trajectory_tracking.py:201) has a kink at 1.5 v = 5: G holds the gradient of
+    the branch that is larger; with_kinks=True additionally returns G2 [B,45,10], the gradient of the OTHER branch, and
+    kink [B,45] = how far the two branches are apart (NaN for rows without a kink) -- at a kink both are subgradients."""
     B = len(x0)
     asm = A.assemble(tab, x0, U)
     X, dX = asm["X"], asm["dX"]
     c = np.full((B, 45), np.nan)
     G = np.zeros((B, 45, 10))
+    G2 = np.zeros((B, 45, 10))
+    kink = np.full((B, 45), np.nan)
     row = np.zeros(B, dtype=np.int64)
     ar = np.arange(B)
     for j in range(1, 6):
@@ -42,11 +47,16 @@ def reference_rows(tab, x0, U, obs_sv, n_obs):
             idx = ar[on]
             c[idx, row[on]] = val[on]
             G[idx, row[on]] = g[on]
+            g2 = -ds - np.where((tg > P.OBS_SAFETY_DIST)[:, None], 0.0, P.MAX_TIME_2_OBS * dv)
+            G2[idx, row[on]] = g2[on]
+            kink[idx, row[on]] = np.abs(tg - P.OBS_SAFETY_DIST)[on]
             row = row + on.astype(np.int64)
         c[ar, row] = v
         G[ar, row] = dv
         row = row + 1
     assert np.array_equal(row, 5 * (7 + n_obs))
+    if with_kinks:
+        return c, G, asm, G2, kink
     return c, G, asm
 
 
@@ -54,7 +64,7 @@ def cost_gradient(asm, U):
     return np.einsum("bk,bki->bi", 2.0 * A.W15 * asm["r"], asm["Jr"]) + U
 
 
-def kkt_residual(c, G, g, U, act_tol=1e-4):
+def kkt_residual(c, G, g, U, act_tol=1e-4, G2=None, kink=None):
     """Per problem: min over lambda >= 0 of | grad J - sum_r lambda_r grad c_r - mu_lo + mu_hi |_inf over the rows and
     bounds within act_tol of active (a slightly generous candidate set only makes the fit easier, never wrong: any
     KKT point of the nonlinear problem has multipliers supported on its active set).  Returns res [B], n_active [B]."""
@@ -67,6 +77,8 @@ def kkt_residual(c, G, g, U, act_tol=1e-4):
         rows = np.where(c[b] <= act_tol)[0]          # NaN compares False
         for r in rows:
             cols.append(G[b, r])
+            if kink is not None and kink[b, r] <= act_tol:     # on the kink of max(5, 1.5 v): both branches count
+                cols.append(G2[b, r])
         for i in np.where(U[b] - lb <= act_tol)[0]:
             e = np.zeros(10); e[i] = 1.0
             cols.append(e)

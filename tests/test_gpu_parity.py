@@ -213,7 +213,7 @@ def test_full_size_batch_properties(gpu_trackers, port_tables):
     assert np.array_equal(part["U"], full["U"][perm]) and np.array_equal(part["status"], full["status"][perm])
     # (b) feasibility from the oracle's rows
     U = full["U"].reshape(B, 10)
-    c, G, asm = kkt.reference_rows(tab, x0, U, obs, n)
+    c, G, asm, G2, kink = kkt.reference_rows(tab, x0, U, obs, n, with_kinks=True)
     cmin = np.nanmin(c, axis=1)
     ok = full["status"] == 0
     assert ok.mean() > 0.9
@@ -234,7 +234,7 @@ def test_full_size_batch_properties(gpu_trackers, port_tables):
     assert np.all(bits[clear_on]) and not np.any(bits[clear_off]) and not np.any(bits[~valid])
     # (d) KKT with multipliers, all solved problems
     g = kkt.cost_gradient(asm, U)
-    res, nact = kkt.kkt_residual(c[ok], G[ok], g[ok], U[ok])
+    res, nact = kkt.kkt_residual(c[ok], G[ok], g[ok], U[ok], G2=G2[ok], kink=kink[ok])
     assert (nact > 0).sum() > 500, "the set must contain problems that sit on constraints"
     assert res.max() <= 1e-5, f"KKT residual {res.max():.3e} at solved problem {np.where(ok)[0][np.argmax(res)]}"
 
