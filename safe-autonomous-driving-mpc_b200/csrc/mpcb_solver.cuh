@@ -688,10 +688,20 @@ MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const 
 //                      certified"), no infeasibility verdict other than the rigorous screens.
 // FIRST_PASS = false: robust ladder with OSQP's infeasibility certificate; inexact Gauss-Newton: the QP of a round is
 //                      solved only as accurately as the previous SQP step warrants (P.qp_forcing).
+// U_start (robust pass only, optional): the controls the first pass had reached when it gave the problem up; the SQP
+// continues from there instead of from the warm start (clipped to the box and to the screen's pins like any start).
 template <bool FIRST_PASS, class ST>
-MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const ST& st, bool live) {
+MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const ST& st, bool live,
+                           const double* U_start = nullptr) {
   SolveOut out{MPCB_MAXITER, 0, 0, false};
   const bool screened = prologue(T, P, pb, st);
+  if (!FIRST_PASS && U_start) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const double u = clipd(U_start[i], P.umin[i & 1], P.umax[i & 1]);
+      pb.U[i] = (i & 1) ? clipd(u, st.blo[i >> 1], st.bhi[i >> 1]) : u;
+    }
+  }
   bool done = !live;
   bool infeasible = screened;
   out.const_infeasible = screened;

@@ -59,7 +59,11 @@ int host_hs_eval(const double* s, const double* y, int K, double dt, int simpson
 #ifdef MPCB_HOST_SOLVER
 #include "mpcb_params.h"
 
+static int* g_pass2_stats = nullptr;   // development: [B][3] rounds, iterations, status of the robust pass alone
+
 extern "C" {
+
+void host_set_pass2_stats(int* p) { g_pass2_stats = p; }
 
 // The tracking solver (solve_one, the code mpcb_solve_kernel runs per thread) on the CPU, one problem at a time,
 // with the same two-pass logic as launch_solve.  `p` may be null (defaults).  Outputs like mpcb_solve_batch;
@@ -74,8 +78,11 @@ int host_solve_batch(const double* s, const double* y, const double* u, int K, i
   DevParams P;
   int rc = derive_params(pp, P);
   if (rc != 0) return rc;
+  const bool carry = getenv("MPCB_CARRY") && atoi(getenv("MPCB_CARRY")) != 0;   // development: pass 2 continues from pass 1's controls
   for (int b = 0; b < B; ++b) {
     int rounds = 0, iters = 0;
+    double U1[NV];
+    bool have1 = false;
     for (int pass = pp.fast_pass ? 1 : 2; pass <= 2; ++pass) {
       Problem pb;
       for (int c = 0; c < 5; ++c) pb.x0[c] = x0[5 * b + c];
@@ -84,8 +91,11 @@ int host_solve_batch(const double* s, const double* y, const double* u, int K, i
       typedef Store<1, 0u> HostStore;
       double buf[HostStore::LOCAL];
       HostStore st(nullptr, buf);
-      SolveOut so = (pass == 1) ? solve_one<true>(T, P, pb, st, true) : solve_one<false>(T, P, pb, st, true);
+      SolveOut so = (pass == 1) ? solve_one<true>(T, P, pb, st, true)
+                                : solve_one<false>(T, P, pb, st, true, (carry && have1) ? U1 : nullptr);
       rounds += so.rounds; iters += so.iters;
+      if (pass == 2 && g_pass2_stats) { g_pass2_stats[3 * b] = so.rounds; g_pass2_stats[3 * b + 1] = so.iters; g_pass2_stats[3 * b + 2] = so.status; }
+      if (pass == 1) { for (int i = 0; i < NV; ++i) U1[i] = pb.U[i]; have1 = true; }
       if (pass == 1 && so.status == MPCB_MAXITER) continue;
       double X[NH + 1][5];
       double cost;
