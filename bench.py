@@ -8,9 +8,12 @@ one batch of BASELINE config 4: the seeded Monte-Carlo set of 65,536 perturbed s
 trajectory3.  Weak scaling: every rank solves its own 65,536 problems (seed + rank); there is no
 collective on the solve path, NCCL only reduces the timing and the statistics.
 
-value     whole-job solves/s with the inputs resident in HBM (CUDA events around every step, max over ranks)
-e2e       the same through the public host API (BatchedTracker.solve_batch_host -> mpcb_solve_batch_host): pinned
-          host buffers in, pinned host buffers out, H2D + kernel + D2H inside the timed region
+value     whole-job solves/s with the inputs resident in HBM: K steps enqueued back to back on three handles / streams
+          (the robust pass of one batch overlaps the first pass of the next), CUDA events around the K steps, max over
+          ranks; `single_call` is one call alone on an idle GPU, `strong` one batch sharded over the ranks + NCCL gather
+e2e       the same through the public host API (BatchedTracker.solve_batch_host_async / wait ->
+          mpcb_solve_batch_host_async): pinned host buffers in, pinned host buffers out, H2D + kernels + D2H of every
+          step inside the timed region, three batches in flight
 roofline  neither HBM nor tensor cores bound this path: it is reported against the FP64 FMA pipe,
           algorithmic flops per SURVEY 8d's formula, peak measured in-process by a register-resident DFMA loop
 --impl reference   the reference's CPU algorithm (oracle port of trajectory_tracking.py solve(): SLSQP ftol=1e-3,
@@ -166,6 +169,91 @@ def run_reference(args):
     return 0
 
 
+N_HANDLES = 3      # device-resident arm: batches in flight (one handle + one stream each); measured on B200: 1 handle
+                   # 0.59 ms per batch, 2: 0.446, 3: 0.415, 4: 0.416 (tools/gpu_pipeline.py)
+N_HANDLES_E2E = 3  # host arm (tools/gpu_e2e_pipe.py): every output 1 / 2 / 3 / 4 handles 1.06 / 0.92 / 0.55 / 0.59 ms per batch,
+                   # closed-loop form 0.71 / 0.51 / 0.44 / 0.44
+N_SETS = 8         # distinct seeded 65,536-problem sets the steps rotate over: 8 x 28 MB of inputs + outputs > 126 MB L2
+
+
+def traffic_from_profile():
+    """dram bytes per step of the two solve launches, from the committed ncu --set full capture of this workload."""
+    f = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if not os.path.exists(f):
+        return None, None
+    t = json.load(open(f))
+    return float(t["first_pass_dram_bytes"]) + float(t["second_pass_dram_bytes"]), t.get("source")
+
+
+def config_extras(M, P, dev, torch):
+    """BASELINE configs 1-3 (closed loops through the reference-shaped B = 1 call, and as a device loop of 4,096
+    vehicles) and config 5 (planner Hermite-Simpson evaluation, x64 tile, with its own HBM roofline)."""
+    from safe_autonomous_driving_mpc_b200 import environment as E
+    out = {}
+    for i in (1, 2, 3):
+        traj = os.path.join(ROOT, "data", f"trajectory{i}.npz")
+        L = M.TrajectoryLoader(traj)
+        T = M.BatchedTracker(L, device=dev.index)
+        sc = {1: None, 2: E.SCENARIO_TRAJECTORY2, 3: E.SCENARIO_TRAJECTORY3}[i]
+        fsm = M.ObstaclesFSM(i > 1, i > 1, scenario=sc)
+        flags = []
+        t0 = time.perf_counter()
+        hx, hu, ht, *_ = M.run_simulation(T, fsm, L, record_flags=flags)
+        wall = time.perf_counter() - t0
+        ht = np.array(ht[5:]) * 1e3
+        st = np.array([f[0] for f in flags])
+        scen = M.make_scenario(2, dynamic_obstacle=0, traffic_light=0) if i == 1 else M.make_scenario(i)
+        nveh = 4096
+        sim = M.BatchedSimulation(T, scen, B=nveh)
+        sim.step(8)
+        torch.cuda.synchronize()
+        sim = M.BatchedSimulation(T, scen, B=nveh)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sim.run(max_steps=len(hu) + 64, check_every=128)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        _, steps, _ = sim.state()
+        out[f"config{i + 0}_trajectory{i}_closed_loop"] = {
+            "steps": int(len(hu)), "status_hist": np.bincount(st, minlength=3).tolist(), "wall_s": wall,
+            "solve_ms_p50": float(np.median(ht)), "solve_ms_p99": float(np.quantile(ht, 0.99)),
+            "device_loop_vehicles": nveh, "device_loop_vehicle_steps_per_s": float(steps.sum() / dt),
+            "reference": "trajectory_tracking.py:377-443"}
+        del sim, T
+    traj3 = os.path.join(ROOT, "data", "trajectory3.npz")
+    L = M.TrajectoryLoader(traj3)
+    T = M.BatchedTracker(L, device=dev.index)
+    z3 = np.load(traj3)
+    N = len(z3["U"])
+    Ev = M.PlannerEvaluator(T, N=N, simpson_sign=+1)
+    z = Ev.pack(z3["X"], z3["U"], z3["S"])
+    tiles = 64
+    zt = torch.from_numpy(np.tile(z, (tiles, 1))).to(dev)
+    lam = torch.from_numpy(np.random.default_rng(7).normal(size=(tiles, N, 5))).to(dev)
+    o = Ev.eval_defects(zt, lam=lam, want_jac=True, want_hess=True)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ms = []
+    for _ in range(12):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Ev.eval_defects(zt, lam=lam, want_jac=True, want_hess=True, out=o)
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    ms = float(np.median(ms[2:]))
+    n_int = tiles * N
+    byt = n_int * (5 + 60 + 144 + 5) * 8 + tiles * (8 * N + 5) * 8      # defects + Jacobian + Hessian blocks out, lam + z in
+    mp_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    hbm_peak = json.load(open(mp_file))["hbm_gbs"] if os.path.exists(mp_file) else 6650.0
+    out["config5_planner_hs_eval_x64"] = {
+        "intervals": n_int, "ms": ms, "intervals_per_s": n_int / ms * 1e3,
+        "roofline": {"bound": "hbm", "achieved": byt / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": byt / ms / 1e6 / hbm_peak, "bytes_per_interval": byt / n_int},
+        "reference": "trajectory_planning.py:183-208"}
+    return out
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -179,7 +267,7 @@ def run_ours(args):
         tab0 = P0.RefTable.from_npz(TRAJ)
         cx0, cobs, cn = P0.monte_carlo_problems(tab0, BATCH)
         cores = host_cores()
-        ns = max(64, min(2048, 24 * cores))
+        ns = 2048                                              # "oracle/CPU timing on the first 2,048 problems"
         v, mean_ms, p99_ms = cpu_reference_rate(cx0[:ns], cobs[:ns], cn[:ns], cores)
         cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"first {ns} problems of the same seeded set, oracle port of the reference solve() as "
@@ -197,66 +285,140 @@ def run_ours(args):
     from oracle import tracker_port as P        # problem generator + cpu_baseline leg only
     B = args.batch
     loader = M.TrajectoryLoader(TRAJ)
-    tracker = M.BatchedTracker(loader, device=local)
+    trackers = [M.BatchedTracker(loader, device=local) for _ in range(max(N_HANDLES, N_HANDLES_E2E))]
+    tracker = trackers[0]
     tab = P.RefTable.from_npz(TRAJ)
-    x0, obs, n = P.monte_carlo_problems(tab, B, seed=P.MC_SEED + rank)
-
-    # ---- device-resident arm ----------------------------------------------------------------------
-    d_x0 = torch.from_numpy(x0).to(dev)
-    d_obs = torch.from_numpy(obs).to(dev)
-    d_n = torch.from_numpy(n).to(dev)
-    out = tracker.solve_batch(d_x0, d_obs, d_n)
-    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
-    torch.cuda.synchronize()
-    peak_tf, _ = tracker.measure_fp64_peak()
+    # weak scaling: every rank its own N_SETS seeded sets (set 0 of rank 0 is THE BASELINE config-4 set)
+    host_sets = [P.monte_carlo_problems(tab, B, seed=P.MC_SEED + rank * N_SETS + k) for k in range(N_SETS)]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(args.warmup, 3)):
-        flush.zero_()
-        tracker.solve_batch(d_x0, d_obs, d_n, out=out)
+    # ---- device-resident arm: N_HANDLES batches in flight on as many streams ----------------------------
+    dsets = [[torch.from_numpy(a).to(dev) for a in hs] for hs in host_sets]
+    outs = [tracker.solve_batch(*ds) for ds in dsets]
+    torch.cuda.synchronize()
+    peak_tf, _ = tracker.measure_fp64_peak()
+    flops_set = [algorithmic_flops(o["iters"].cpu().numpy(), hs[2].astype(np.float64)) for o, hs in zip(outs, host_sets)]
+    streams = [torch.cuda.Stream(dev) for _ in range(N_HANDLES)]
+    main = torch.cuda.current_stream(dev)
+
+    def pipelined(nsteps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(main)
+        for s_ in streams:
+            s_.wait_event(e0)
+        for i in range(nsteps):
+            k = i % N_SETS
+            trackers[i % N_HANDLES].solve_batch(*dsets[k], out=outs[k], stream=streams[i % N_HANDLES].cuda_stream)
+        for s_ in streams:
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            main.wait_event(ev)
+        e1.record(main)
+        return e0, e1
+
+    for _ in range(2):
+        pipelined(max(args.warmup, 3))
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    launches0 = tracker.launch_count()
-    evs = []
+    launches0 = sum(t.launch_count() for t in trackers)
     barrier()
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        tracker.solve_batch(d_x0, d_obs, d_n, out=out)
-        e1.record()
-        evs.append((e0, e1))
+    e0, e1 = pipelined(args.steps)
     barrier()
     t_wall = time.perf_counter() - t_wall0
-    step_ms = [a.elapsed_time(b) for a, b in evs]
-    pass_ms = tracker.last_pass_ms()
-    launches = tracker.launch_count() - launches0
-    ms_dev = float(np.mean(step_ms))
+    ms_dev = e0.elapsed_time(e1) / args.steps
+    launches = sum(t.launch_count() for t in trackers) - launches0
+    flops_step = float(np.mean([flops_set[i % N_SETS] for i in range(args.steps)]))
 
-    # ---- end-to-end arm: public host API, pinned buffers, copies inside the timed region -----------
-    pin = {k: M.tracker.PinnedBuffer(a.shape, a.dtype) for k, a in (("x0", x0), ("obs", obs), ("n", n))}
-    pin["x0"].array[...] = x0
-    pin["obs"].array[...] = obs
-    pin["n"].array[...] = n
-    for _ in range(3):
-        tracker.solve_batch_host(pin["x0"].array, pin["obs"].array, pin["n"].array)
-    barrier()
-    e2e_t = []
-    for _ in range(args.steps):
+    # ---- one call alone (latency of a whole batch, per-pass times), L2 flushed between calls ---------------
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    single = []
+    for it in range(3 + 10):
         flush.zero_()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        tracker.solve_batch(*dsets[0], out=outs[0])
+        a1.record()
         torch.cuda.synchronize()
+        if it >= 3:
+            single.append(a0.elapsed_time(a1))
+    pass_ms = tracker.last_pass_ms()
+    ms_single = float(np.mean(single))
+
+    # ---- strong scaling: ONE 65,536-problem batch (rank 0's set 0) sharded over the ranks, results all-gathered ----
+    x0s, obss, ns_ = P.monte_carlo_problems(tab, B, seed=P.MC_SEED)
+    lo, hi = M.sharding.shard_bounds(B, rank, world)
+    sx0, sobs, sn = (torch.from_numpy(np.ascontiguousarray(a[lo:hi])).to(dev) for a in (x0s, obss, ns_))
+    sout = tracker.solve_batch(sx0, sobs, sn)
+    strong_solve, strong_gather = [], []
+    for it in range(3 + 10):
+        flush.zero_()
+        barrier()
+        a0, a1, a2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        a0.record()
+        tracker.solve_batch(sx0, sobs, sn, out=sout)
+        a1.record()
+        full = M.sharding.gather_device(sout["U"], sout["status"], B)        # NCCL all_gather, after the solve
+        a2.record()
+        torch.cuda.synchronize()
+        if it >= 3:
+            strong_solve.append(a0.elapsed_time(a1))
+            strong_gather.append(a1.elapsed_time(a2))
+    sp = tracker.last_pass_ms()
+    strong_ms = float(np.mean(strong_solve)) + float(np.mean(strong_gather))
+    del full
+
+    # ---- end-to-end arm: public host API (asynchronous form, N_HANDLES_E2E batches in flight), pinned host buffers,
+    # H2D + kernels + D2H inside the timed region; full outputs, and the closed-loop form (U*[0] + status) beside it ----
+    PB = M.tracker.PinnedBuffer
+    keep = []
+
+    def pinned(a):
+        b_ = PB(a.shape, a.dtype)
+        b_.array[...] = a
+        keep.append(b_)
+        return b_.array
+
+    def pinned_out(spec):
+        o_ = {}
+        for k_, (shp, dt_) in spec.items():
+            b_ = PB(shp, dt_)
+            keep.append(b_)
+            o_[k_] = b_.array
+        return o_
+
+    FULL = dict(U=((B, 5, 2), np.float64), Xpred=((B, 6, 5), np.float64), obj=((B,), np.float64),
+                status=((B,), np.int32), iters=((B, 2), np.int32), cmin=((B,), np.float64), active=((B,), np.uint64))
+    U0 = dict(u0=((B, 2), np.float64), status=((B,), np.int32))
+    nh = N_HANDLES_E2E
+    pins = [[pinned(a) for a in host_sets[k]] for k in range(nh)]
+
+    def e2e_run(spec_outs, nsteps):
         t0 = time.perf_counter()
-        res = tracker.solve_batch_host(pin["x0"].array, pin["obs"].array, pin["n"].array)
-        e2e_t.append(time.perf_counter() - t0)
-    barrier()
+        for i in range(nsteps):
+            k = i % nh
+            if i >= nh:
+                trackers[k].wait()
+            trackers[k].solve_batch_host_async(*pins[k], spec_outs[k])
+        for k in range(nh):
+            trackers[k].wait()
+        return (time.perf_counter() - t0) / nsteps * 1e3
+
+    e2e_ms = {}
+    for name, spec in (("full", FULL), ("closed_loop", U0)):
+        po = [pinned_out(spec) for _ in range(nh)]
+        e2e_run(po, 3 * nh)
+        barrier()
+        e2e_ms[name] = e2e_run(po, args.steps)
+        barrier()
+        if name == "full":
+            res = po[0]
     clocks = sampler.stop()
-    ms_e2e = float(np.mean(e2e_t) * 1e3)
     h2d = B * (40 + 32 + 4)
     d2h = B * (80 + 240 + 8 + 4 + 8 + 8 + 8)
 
@@ -264,13 +426,17 @@ def run_ours(args):
     iters = res["iters"].copy()
     # NCCL is used only here, after the timed regions: MAX of the times, SUM of the statistics (no collective on the
     # solve path)
-    tot = M.sharding.reduce_stats(status, iters, ms_dev, device=dev)
-    tot_e2e = M.sharding.reduce_stats(status, iters, ms_e2e, device=dev)
-    ms_dev_max, ms_e2e_max = tot["ms_max"], tot_e2e["ms_max"]
+    red = {k: M.sharding.reduce_stats(status, iters, v, device=dev)
+           for k, v in (("dev", ms_dev), ("single", ms_single), ("e2e", e2e_ms["full"]), ("e2e_cl", e2e_ms["closed_loop"]),
+                        ("strong", strong_ms), ("strong_first_max", sp[0]), ("strong_second_max", sp[1]),
+                        ("strong_first_min", -sp[0]), ("strong_second_min", -sp[1]))}
+    tot = red["dev"]
+    ms_dev_max = tot["ms_max"]
     hist = [tot["solved"], tot["maxiter"], tot["infeasible"]]
 
     if rank == 0:
         # single-solve latency through the reference-shaped call (B = 1, host API, includes launch + copies)
+        x0, obs, n = host_sets[0]
         lat = []
         for i in range(320):
             o = [{"s": float(obs[i, k, 0]), "v": float(obs[i, k, 1]), "type": "car"} for k in range(int(n[i]))]
@@ -278,42 +444,65 @@ def run_ours(args):
             tracker.solve(x0[i], o)
             lat.append((time.perf_counter() - t0) * 1e3)
         lat = np.array(lat[20:])
-        flops = algorithmic_flops(iters, n.astype(np.float64))
-        achieved = flops / (ms_dev * 1e-3) / 1e12
+        achieved = flops_step / (ms_dev * 1e-3) / 1e12
         hbm_bytes = B * 416.0
         mp_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
         hbm_peak = json.load(open(mp_file))["hbm_gbs"] if os.path.exists(mp_file) else 6650.0
+        traffic, traffic_src = traffic_from_profile()
+        iters0 = outs[0]["iters"].cpu().numpy()
         roofline = {"bound": "fp64", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of the two solve launches of one step, from the
-                    # ncu --set full capture of this workload (profiles/r01_v6_solve_kernels_ncu.txt; the r01 v5
-                    # capture of the same kernels read 149.5 MB: how much thread-local state L2 writes back varies from
-                    # run to run); algorithmic bytes are 416 B/solve = 27.3 MB
-                    "traffic": 72.8e6 + 0.65e6,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the two solve launches of one step, read from the
+                    # committed ncu --set full capture of this workload; algorithmic bytes are 416 B/solve = 27.3 MB
+                    "traffic": traffic, "traffic_source": traffic_src,
                     "note": "path is bound by the FP64 FMA pipe, not HBM or tensor cores (SURVEY 8d); peak = DFMA "
                             "loop measured in this run (mpcb_measure_fp64_peak); flops per SURVEY 8d formula with "
-                            "the kernel's own per-problem round/iteration counts",
-                    "mean_rounds": float(iters[:, 0].mean()), "mean_admm_iters": float(iters[:, 1].mean()),
+                            "the kernel's own per-problem round/iteration counts, over the step time of the timed "
+                            "region (batches in flight overlap, so no kernel is timed alone there)",
+                    "dominant_kernel": {"name": "mpcb_solve_kernel<true> (first pass, thread per problem)",
+                                        "ms_alone": pass_ms[0],
+                                        "achieved_alone": algorithmic_flops(iters0, host_sets[0][2].astype(np.float64))
+                                        / ((pass_ms[0] + pass_ms[1]) * 1e-3) / 1e12},
+                    "mean_rounds": float(iters0[:, 0].mean()), "mean_admm_iters": float(iters0[:, 1].mean()),
                     "hbm": {"achieved": hbm_bytes / (ms_dev * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                             "frac": hbm_bytes / (ms_dev * 1e-3) / 1e9 / hbm_peak,
                             "peak_source": "measured" if os.path.exists(mp_file) else "fallback"}}
         line = {"metric": METRIC, "value": B * world / (ms_dev_max * 1e-3), "unit": UNIT, "n_gpus": world,
-                "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_dev_max,
+                "steps": args.steps, "warmup": 2 * max(args.warmup, 3), "ms_per_step": ms_dev_max,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
                 "config": {"workload": WORKLOAD, "batch_per_gpu": B, "horizon": 5, "n_var": 10,
-                           "l2": "flushed between timed steps (256 MiB write)", "parallelism": f"batch-sharded x{world}"},
-                "e2e": {"value": B * world / (ms_e2e_max * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e_max},
+                           "l2": f"inputs larger than L2: the steps rotate over {N_SETS} seeded sets per GPU "
+                                 f"({N_SETS} x {B * 416 / 1e6:.0f} MB of inputs and outputs against 126 MB of L2)",
+                           "in_flight": f"{N_HANDLES} batches (one handle and stream each): the robust pass of one batch "
+                                        "overlaps the first pass of the next",
+                           "parallelism": f"batch-sharded x{world}"},
+                "e2e": {"value": B * world / (red["e2e"]["ms_max"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                        "d2h_bytes_per_step": d2h, "ms_per_step": red["e2e"]["ms_max"], "copies_declared": True,
+                        "api": f"BatchedTracker.solve_batch_host_async / wait, {nh} batches in flight, every output",
+                        "closed_loop_form": {"value": B * world / (red["e2e_cl"]["ms_max"] * 1e-3), "unit": UNIT,
+                                             "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": B * 20,
+                                             "ms_per_step": red["e2e_cl"]["ms_max"],
+                                             "note": "U*[0] and status only: what run_simulation consumes"}},
                 "gpu_launches": int(launches) * world,
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+                "single_call": {"ms": red["single"]["ms_max"], "solves_per_s": B * world / (red["single"]["ms_max"] * 1e-3),
+                                "first_ms": pass_ms[0], "second_ms": pass_ms[1], "second_pass_problems": pass_ms[2],
+                                "note": "one mpcb_solve_batch call alone on an idle GPU, L2 flushed before it (256 MiB "
+                                        "write): the robust pass's latency tail is exposed"},
+                "strong": {"problems": B, "ms": red["strong"]["ms_max"], "solves_per_s": B / (red["strong"]["ms_max"] * 1e-3),
+                           "gather_ms": float(np.mean(strong_gather)),
+                           "first_ms_max": red["strong_first_max"]["ms_max"], "first_ms_min": -red["strong_first_min"]["ms_max"],
+                           "second_ms_max": red["strong_second_max"]["ms_max"],
+                           "second_ms_min": -red["strong_second_min"]["ms_max"],
+                           "note": "ONE 65,536-problem batch, shard [g*B/G, (g+1)*B/G) per GPU, U and status all-gathered "
+                                   "with NCCL after the solve (gather_ms: rank 0)"},
                 "latency": {"B": 1, "p50_ms": float(np.median(lat)), "p99_ms": float(np.quantile(lat, 0.99)),
                             "n": int(len(lat)), "path": "BatchedTracker.solve (host API, includes copies + launch)"},
                 "status_hist": {"solved": hist[0], "maxiter": hist[1], "infeasible": hist[2]},
-                "passes": {"first_ms": pass_ms[0], "second_ms": pass_ms[1], "second_pass_problems": pass_ms[2],
-                           "note": "last timed step on rank 0: two-level first pass over all problems, robust ladder "
-                                   "pass over the uncertified leftovers"},
                 "wall_s_timed_region": t_wall}
+        if not args.no_extras:
+            line["configs"] = config_extras(M, P, dev, torch)
         print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.barrier()
@@ -338,6 +527,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=BATCH)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the closed-loop / planner lines of configs 1-3 and 5")
     args = ap.parse_args()
     global _OUT
     _OUT = _quiet_stdout()

@@ -141,6 +141,18 @@ int mpcb_solve_batch_host(mpcb_handle h, int B, const double* x0, const double* 
 int mpcb_solve_batch_host_u0(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
                              double* u0_out, int* status_out, double* obj_out);
 
+/* Asynchronous form of the two host entry points above, for callers that keep several batches in flight (one handle per
+ * batch in flight): enqueues the host-to-device copies, the solve and the device-to-host copies on the handle's own
+ * streams and returns; the results are in the caller's buffers after mpcb_wait(h).  Buffers must be page-locked
+ * (mpcb_host_alloc) for the copies to run asynchronously and must stay untouched until mpcb_wait returns.  U_out may be
+ * NULL when u0_out is given (closed-loop form); any other output may be NULL.  With three handles the copies of one
+ * batch overlap the kernels of the next and the latency tail of the robust pass of the one before (measured on B200:
+ * see DESIGN.md).  Batches of up to 2,048 problems go through the packed staging path and complete inside the call. */
+int mpcb_solve_batch_host_async(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
+                                double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,
+                                double* cmin_out, unsigned long long* active_out, double* u0_out);
+int mpcb_wait(mpcb_handle h);
+
 /* Evaluate the model functions at given controls (no optimisation).  DEVICE pointers, async on stream.
  *   U [B][10] -> Xpred_out [B][6][5] (predict), cost_out [B] (cost), cons_out [B][45] (constraints_wrapper rows,
  *   first 5*(7+n_obs[b]) valid, rest NaN), lin_out [B][150] (the solver's linearisation at U, packed: Gauss-Newton

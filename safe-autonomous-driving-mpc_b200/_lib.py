@@ -79,6 +79,8 @@ SYMBOLS = {
     "mpcb_solve_batch": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 10 + [C.c_void_p]),
     "mpcb_solve_batch_host": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 10),
     "mpcb_solve_batch_host_u0": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 6),
+    "mpcb_solve_batch_host_async": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 11),
+    "mpcb_wait": (C.c_int, [C.c_void_p]),
     "mpcb_eval_batch": (C.c_int, [C.c_void_p, C.c_int] + [C.c_void_p] * 9 + [C.c_void_p]),
     "mpcb_host_alloc": (C.c_int, [C.POINTER(C.c_void_p), C.c_ulonglong]),
     "mpcb_host_free": (C.c_int, [C.c_void_p]),

@@ -6,6 +6,7 @@ used only afterwards, to gather results and to reduce statistics:
 
     shard_bounds      the partition
     solve_sharded     scatter-free sharded solve + optional gather of (U, status, obj) to every rank
+    gather_device     all-gather of the shards' device-resident U / status (NCCL), no host round trip
     reduce_stats      status histogram / iteration sums (SUM) and timings (MAX) over ranks
 """
 import numpy as np
@@ -72,3 +73,33 @@ def solve_sharded(solve_fn, x0, obs_sv, n_obs, group=None, gather=True, device=N
         full[key] = cat
     return dict(U=full["U"].reshape(B, 5, 2), status=full["status"].reshape(B), obj=full["obj"].reshape(B),
                 iters=full["iters"].reshape(B, 2)), (lo, hi)
+
+
+def gather_device(U_shard, status_shard, B, group=None):
+    """All-gather of device-resident shard results after a sharded solve: ``U_shard`` [b,5,2] f64 and ``status_shard``
+    [b] i32 of this rank's contiguous shard of a batch of B -> (U [B,5,2], status [B]) on every rank, in batch order.
+    One collective per array (``all_gather_into_tensor`` when the shards are equal, padded ``all_gather`` otherwise);
+    never on the solve path."""
+    import torch
+    dist = _dist()
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    if world == 1:
+        return U_shard, status_shard
+    sizes = [shard_bounds(B, g, world) for g in range(world)]
+    b = U_shard.shape[0]
+    if all(h - l == b for l, h in sizes):
+        U = torch.empty((B, 5, 2), dtype=U_shard.dtype, device=U_shard.device)
+        st = torch.empty((B,), dtype=status_shard.dtype, device=status_shard.device)
+        dist.all_gather_into_tensor(U, U_shard.contiguous(), group=group)
+        dist.all_gather_into_tensor(st, status_shard.contiguous(), group=group)
+        return U, st
+    pad = max(h - l for l, h in sizes)
+    outs = []
+    for a in (U_shard.reshape(b, -1), status_shard.reshape(b, 1)):
+        mine = torch.zeros((pad, a.shape[1]), dtype=a.dtype, device=a.device)
+        mine[:b] = a
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        outs.append(torch.cat([p[: h - l] for p, (l, h) in zip(parts, sizes)]))
+    return outs[0].reshape(B, 5, 2), outs[1].reshape(B)

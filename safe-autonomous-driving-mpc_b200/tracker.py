@@ -228,6 +228,25 @@ class BatchedTracker:
               "mpcb_solve_batch_host_u0")
         return out
 
+    def solve_batch_host_async(self, x0, obs_sv, n_obs, out):
+        """Asynchronous host call (mpcb_solve_batch_host_async): ``x0`` [B,5] f64, ``obs_sv`` [B,2,2] f64, ``n_obs`` [B] i32
+        and the arrays of ``out`` (any of U, Xpred, obj, status, iters, cmin, active, u0; U or u0 required) must be
+        C-contiguous page-locked arrays (``PinnedBuffer``) and stay untouched until ``wait()``.  One batch in flight per
+        tracker; use several trackers to overlap copies and kernels of consecutive batches."""
+        h = self._need()
+        B = x0.shape[0]
+        for a in (x0, obs_sv, n_obs, *out.values()):
+            assert a.flags["C_CONTIGUOUS"]
+        assert x0.dtype == np.float64 and obs_sv.dtype == np.float64 and n_obs.dtype == np.int32
+        g = lambda k: _dp(out[k]) if k in out else None   # noqa: E731
+        check(self._lib.mpcb_solve_batch_host_async(h, B, _dp(x0), _dp(obs_sv), _dp(n_obs), g("U"), g("Xpred"), g("obj"),
+                                                    g("status"), g("iters"), g("cmin"), g("active"), g("u0")),
+              "mpcb_solve_batch_host_async")
+        return out
+
+    def wait(self):
+        check(self._lib.mpcb_wait(self._need()), "mpcb_wait")
+
     def solve_batch(self, x0, obs_sv, n_obs, out=None, stream=None):
         """Device tensors in, device tensors out (torch used only for memory + stream hand-off).
         Asynchronous on ``stream`` (default: torch's current stream)."""

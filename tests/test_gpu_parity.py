@@ -393,3 +393,45 @@ def test_closed_loop_form_of_the_host_entry(gpu_trackers, port_tables):
             assert np.array_equal(r["status"], full["status"]) and np.array_equal(r["obj"], full["obj"]), (B, rep)
         r = T.solve_batch_host_u0(x0[:B], obs[:B], n[:B], pinned_out=False)
         assert np.array_equal(r["u0"], full["U"][:, 0, :]) and "obj" not in r
+
+
+def test_asynchronous_host_entry_with_batches_in_flight(gpu_trackers, port_tables):
+    """mpcb_solve_batch_host_async / mpcb_wait with three handles in flight (the form bench.py's e2e arm uses): every
+    batch comes back bit-identical to the synchronous call on the same problems -- every output and the closed-loop form
+    (U*[0] + status), first calls, captured call and graph replays, with the input buffers rewritten between rounds."""
+    import safe_autonomous_driving_mpc_b200 as M
+    from oracle import tracker_port as P
+    L, T = gpu_trackers[3]
+    B, nh = 9000, 3
+    x0, obs, n = P.monte_carlo_problems(port_tables[3], 2 * nh * B)
+    PB = M.tracker.PinnedBuffer
+    Ts = [M.BatchedTracker(L) for _ in range(nh)]
+    full_spec = dict(U=((B, 5, 2), np.float64), Xpred=((B, 6, 5), np.float64), obj=((B,), np.float64),
+                     status=((B,), np.int32), iters=((B, 2), np.int32), cmin=((B,), np.float64), active=((B,), np.uint64))
+    cl_spec = dict(u0=((B, 2), np.float64), status=((B,), np.int32))
+    refs = [{k: v.copy() for k, v in T.solve_batch_host(x0[j * B:(j + 1) * B], obs[j * B:(j + 1) * B], n[j * B:(j + 1) * B]).items()}
+            for j in range(2 * nh)]
+    for spec in (full_spec, cl_spec):
+        bufs = [dict(x0=PB((B, 5), np.float64), obs=PB((B, 2, 2), np.float64), n=PB((B,), np.int32)) for _ in range(nh)]
+        outs = [{k: PB(shp, dt) for k, (shp, dt) in spec.items()} for _ in range(nh)]
+        for rnd in range(4):                                   # 0 direct, 1 captured, 2.. replayed; data alternates
+            js = [(rnd % 2) * nh + k for k in range(nh)]
+            for k, j in enumerate(js):
+                bufs[k]["x0"].array[...] = x0[j * B:(j + 1) * B]
+                bufs[k]["obs"].array[...] = obs[j * B:(j + 1) * B]
+                bufs[k]["n"].array[...] = n[j * B:(j + 1) * B]
+                for o in outs[k].values():
+                    o.array[...] = 0
+                Ts[k].solve_batch_host_async(bufs[k]["x0"].array, bufs[k]["obs"].array, bufs[k]["n"].array,
+                                             {kk: o.array for kk, o in outs[k].items()})
+            for k, j in enumerate(js):
+                Ts[k].wait()
+                for kk, o in outs[k].items():
+                    want = refs[j]["U"][:, 0, :] if kk == "u0" else refs[j][kk]
+                    assert np.array_equal(o.array, want), (kk, rnd, k)
+    # small batches complete inside the call (packed staging path)
+    o = dict(u0=np.zeros((5, 2)), status=np.zeros(5, np.int32))
+    Ts[0].solve_batch_host_async(x0[:5].copy(), obs[:5].copy(), n[:5].copy(), o)
+    small = T.solve_batch_host(x0[:5], obs[:5], n[:5])        # same execution shape (one warp per problem)
+    assert np.array_equal(o["u0"], small["U"][:, 0, :]) and np.array_equal(o["status"], small["status"])
+    Ts[0].wait()

@@ -45,6 +45,12 @@ def _worker(rank, world, port, B, q):
         x0, obs, n = P.monte_carlo_problems(tab, B)
         full, (lo, hi) = S.solve_sharded(solve, x0, obs, n, gather=True)
         stats = S.reduce_stats(full["status"][lo:hi], full["iters"][lo:hi], ms=10.0 + rank)
+        # the tensor-level gather bench.py's strong-scaling block uses (NCCL there, gloo here): ragged and equal shards
+        import torch
+        for Bg in (B, B - 1):
+            l2, h2 = S.shard_bounds(Bg, rank, world)
+            Ug, sg = S.gather_device(torch.from_numpy(full["U"][l2:h2].copy()), torch.from_numpy(full["status"][l2:h2].copy()), Bg)
+            assert np.array_equal(Ug.numpy(), full["U"][:Bg]) and np.array_equal(sg.numpy(), full["status"][:Bg])
         q.put((rank, lo, hi, full["U"], full["status"], full["obj"], stats))
     finally:
         dist.destroy_process_group()
