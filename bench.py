@@ -8,7 +8,7 @@ one batch of BASELINE config 4: the seeded Monte-Carlo set of 65,536 perturbed s
 trajectory3.  Weak scaling: every rank solves its own 65,536 problems (seed + rank); there is no
 collective on the solve path, NCCL only reduces the timing and the statistics.
 
-value     whole-job solves/s with the inputs resident in HBM: K steps enqueued back to back on three handles / streams
+value     whole-job solves/s with the inputs resident in HBM: K steps enqueued back to back on two handles / streams
           (the robust pass of one batch overlaps the first pass of the next), CUDA events around the K steps, max over
           ranks; `single_call` is one call alone on an idle GPU, `strong` one batch sharded over the ranks + NCCL gather
 e2e       the same through the public host API (BatchedTracker.solve_batch_host_async / wait ->
@@ -169,8 +169,8 @@ def run_reference(args):
     return 0
 
 
-N_HANDLES = 3      # device-resident arm: batches in flight (one handle + one stream each); measured on B200: 1 handle
-                   # 0.59 ms per batch, 2: 0.446, 3: 0.415, 4: 0.416 (tools/gpu_pipeline.py)
+N_HANDLES = 2      # device-resident arm: batches in flight (one handle + one stream each); measured on B200: 1 handle
+                   # 0.556 ms per batch, 2: 0.396, 3: 0.410, 4: 0.444 (tools/gpu_pipeline.py)
 N_HANDLES_E2E = 3  # host arm (tools/gpu_e2e_pipe.py): every output 1 / 2 / 3 / 4 handles 1.06 / 0.92 / 0.55 / 0.59 ms per batch,
                    # closed-loop form 0.71 / 0.51 / 0.44 / 0.44
 N_SETS = 8         # distinct seeded 65,536-problem sets the steps rotate over: 8 x 28 MB of inputs + outputs > 126 MB L2

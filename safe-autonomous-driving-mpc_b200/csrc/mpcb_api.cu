@@ -29,6 +29,30 @@ namespace mpcb {
 constexpr int SOLVE_THREADS = MPCB_SOLVE_THREADS;
 using SolveStore = Store<(MPCB_STORE_MASK != 0 ? SOLVE_THREADS : 1), MPCB_STORE_MASK>;
 constexpr size_t SOLVE_SMEM = sizeof(double) * SolveStore::SHARED * SOLVE_THREADS;
+// First pass, one instantiation per obstacle count (the batch is partitioned by n_obs, see mpcb_classify_kernel): which
+// arrays sit in shared memory (bits as in mpcb_solver.cuh).  Fewer obstacle slots leave room for more of the working set:
+//   2 obstacles  v, rho, hio                      (41 + 41 + 18 = 100 doubles per thread)
+//   1 obstacle   v, rho, hio, q, lane_c           (32 + 32 + 9 + 18 = 91)
+//   none         v, rho, D, O, q, lane_c          (23 + 23 + 40 + 18 = 104: the lane sensitivities are read seven times
+//                                                  per round; with H there instead 0.345 ms, with D, O 0.308 ms)
+// Measured on B200, 65,536 Monte-Carlo problems (50 % without obstacle, 40 % one, 10 % two): first pass 0.36 ms
+// unpartitioned -> 0.31 ms; other placements for the one- and two-obstacle classes within +-2 % (tools/variants.py).
+#ifndef MPCB_CLS_MASK0
+#define MPCB_CLS_MASK0 (1u | 2u | 8u | 32u)
+#endif
+#ifndef MPCB_CLS_MASK1
+#define MPCB_CLS_MASK1 (1u | 2u | 4u | 32u)
+#endif
+#ifndef MPCB_CLS_MASK2
+#define MPCB_CLS_MASK2 7u
+#endif
+template <int NOBS> struct ClsCfg;
+template <> struct ClsCfg<0> { typedef Store<SOLVE_THREADS, MPCB_CLS_MASK0, 0> St; };
+template <> struct ClsCfg<1> { typedef Store<SOLVE_THREADS, MPCB_CLS_MASK1, 1> St; };
+template <> struct ClsCfg<2> { typedef Store<SOLVE_THREADS, MPCB_CLS_MASK2, 2> St; };
+constexpr int cmax3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+constexpr size_t CLS_SMEM = sizeof(double) * SOLVE_THREADS * cmax3(ClsCfg<0>::St::SHARED, ClsCfg<1>::St::SHARED, ClsCfg<2>::St::SHARED);
+constexpr int CLS_HDR = 4;                // class-list header: three counts, pad; then three lists of B indices each
 constexpr int EVAL_THREADS = 128;
 
 // Device pointers of one solve call (mpcb_solve_batch's arguments), handed to the kernels as one block.
@@ -173,6 +197,79 @@ mpcb_solve_kernel(const __grid_constant__ DevTable T, const __grid_constant__ De
   SolveOut so = solve_one<FIRST_PASS>(T, P, pb, st, live);
   if (!live) return;
   finalize<FIRST_PASS>(T, P, pb, so, b, io.accumulate != 0, io, fb_list, fb_count);
+}
+
+// ------------------------------------------------------------------------------------------------
+// First pass of a large batch, specialised by obstacle count.  mpcb_classify_kernel partitions the work (all problems,
+// or the caller's list) into three index lists by n_obs; mpcb_solve_cls_kernel gives every CTA 128 problems of ONE class
+// -- the classes with more rows first, so that the longest CTAs start first -- and runs the instantiation of the solver
+// that has exactly that many obstacle slots.  A problem's answer does not depend on which CTA it lands in.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mpcb_classify_kernel(int B, const int* __restrict__ idx, const int* __restrict__ n_idx, const int* __restrict__ n_obs,
+                     int* __restrict__ cls) {
+  const int n_work = idx ? min(*n_idx, B) : B;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = t < n_work;
+  const int b = live ? (idx ? idx[t] : t) : 0;
+  const int c = live ? min(max(n_obs[b], 0), 2) : -1;
+  const unsigned lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const unsigned m = __ballot_sync(0xffffffffu, c == k);
+    if (m == 0u) continue;
+    int base = 0;
+    const int leader = __ffs(m) - 1;
+    if ((int)lane == leader) base = atomicAdd(cls + k, __popc(m));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (c == k) cls[CLS_HDR + (size_t)k * B + base + __popc(m & ((1u << lane) - 1u))] = b;
+  }
+}
+
+template <int NOBS>
+__device__ __forceinline__ void solve_cls_body(const DevTable& T, const DevParams& P, const SolveIO& io, const int* __restrict__ list,
+                                               int n_work, int t0, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  typedef typename ClsCfg<NOBS>::St St;
+  const int t = t0 + threadIdx.x;
+  const bool live = t < n_work;
+  const int b = live ? list[t] : 0;
+  Problem pb;
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) pb.x0[c] = io.x0[(size_t)b * 5 + c];
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      pb.obs[k][0] = (k < NOBS) ? io.obs_sv[(size_t)b * 4 + 2 * k] : 0.0;
+      pb.obs[k][1] = (k < NOBS) ? io.obs_sv[(size_t)b * 4 + 2 * k + 1] : 0.0;
+    }
+    pb.n_obs = NOBS;
+  } else {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) pb.x0[c] = 0.0;
+    pb.obs[0][0] = pb.obs[0][1] = pb.obs[1][0] = pb.obs[1][1] = 0.0;
+    pb.n_obs = 0;
+  }
+  extern __shared__ double solve_smem[];
+  double solve_local[St::LOCAL];
+  const St st(solve_smem + threadIdx.x, solve_local);
+  SolveOut so = solve_one<true>(T, P, pb, st, live);
+  if (!live) return;
+  finalize<true>(T, P, pb, so, b, io.accumulate != 0, io, fb_list, fb_count);
+}
+
+__global__ void __launch_bounds__(SOLVE_THREADS, MPCB_SOLVE_CTAS)
+mpcb_solve_cls_kernel(const __grid_constant__ DevTable T, const __grid_constant__ DevParams P, int B,
+                      const __grid_constant__ SolveIO io, const int* __restrict__ cls, int* __restrict__ fb_list,
+                      int* __restrict__ fb_count) {
+  const int n2 = cls[2], n1 = cls[1], n0 = cls[0];
+  const int c2 = (n2 + SOLVE_THREADS - 1) / SOLVE_THREADS, c1 = (n1 + SOLVE_THREADS - 1) / SOLVE_THREADS,
+            c0 = (n0 + SOLVE_THREADS - 1) / SOLVE_THREADS;
+  int blk = blockIdx.x;                                                       // CTA-uniform from here on
+  if (blk < c2) { solve_cls_body<2>(T, P, io, cls + CLS_HDR + (size_t)2 * B, n2, blk * SOLVE_THREADS, fb_list, fb_count); return; }
+  blk -= c2;
+  if (blk < c1) { solve_cls_body<1>(T, P, io, cls + CLS_HDR + (size_t)1 * B, n1, blk * SOLVE_THREADS, fb_list, fb_count); return; }
+  blk -= c1;
+  if (blk < c0) solve_cls_body<0>(T, P, io, cls + CLS_HDR, n0, blk * SOLVE_THREADS, fb_list, fb_count);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -508,7 +605,7 @@ int mpcb_create(mpcb_handle* out, const mpcb_params* p, mpcb_table_handle t, int
   if ((e = cudaEventCreate(&c->ev1)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreate(&c->ev_mid)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
   if ((e = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate"));
-  if ((e = cudaFuncSetAttribute(mpcb_solve_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM)) != cudaSuccess ||
+  if ((e = cudaFuncSetAttribute(mpcb_solve_cls_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CLS_SMEM)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(mpcb_solve_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SOLVE_SMEM)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(mpcb_coop_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM)) != cudaSuccess ||
       (e = cudaFuncSetAttribute(mpcb_coop_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)COOP_SMEM)) != cudaSuccess)
@@ -560,6 +657,7 @@ int mpcb_destroy(mpcb_handle h) {
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
   if (h->ws) cudaFree(h->ws);
   if (h->fb) cudaFree(h->fb);
+  if (h->cls) cudaFree(h->cls);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_mid) cudaEventDestroy(h->ev_mid);
@@ -582,7 +680,11 @@ static const int HOST_CHUNKS = MPCB_HOST_CHUNKS;   // parts of a large host batc
 static int ensure_fb(mpcb_handle h, int B) {
   if (!h->params.fast_pass || B + FB_HDR * HOST_CHUNKS <= h->fb_cap) return MPCB_OK;
   if (h->fb) { CK(cudaFree(h->fb)); h->fb = nullptr; h->fb_cap = 0; }
+  if (h->cls) { CK(cudaFree(h->cls)); h->cls = nullptr; }
   if (cudaMalloc(&h->fb, sizeof(int) * ((size_t)B + FB_HDR * HOST_CHUNKS)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
+  // class lists of the first pass: a part whose work list starts at fb + o keeps its header and three lists at cls + 3 o
+  // (FB_HDR == CLS_HDR, so the slices of the parts of a chunked host call do not overlap)
+  if (cudaMalloc(&h->cls, sizeof(int) * 3 * ((size_t)B + FB_HDR * HOST_CHUNKS)) != cudaSuccess) { cudaGetLastError(); return MPCB_ERR_NOMEM; }
   h->fb_cap = B + FB_HDR * HOST_CHUNKS;
   return MPCB_OK;
 }
@@ -621,7 +723,16 @@ static int launch_solve(mpcb_handle h, int B, const SolveIO& io, cudaStream_t st
       const int g1 = std::min((B + COOP_WARPS - 1) / COOP_WARPS, h->n_sm * COOP_CTAS);
       mpcb_coop_kernel<true><<<g1, COOP_WARPS * 32, COOP_SMEM, st>>>(h->dt, h->dp, B, io, fb_list, fb_count, fb + 1);
     } else {
-      mpcb_solve_kernel<true><<<grid, SOLVE_THREADS, SOLVE_SMEM, st>>>(h->dt, h->dp, B, io, fb_list, fb_count);
+      // partition by obstacle count, then one CTA per 128 problems of one class (at most two partly filled CTAs more
+      // than the unpartitioned grid)
+      int* cls = h->cls + (fb - h->fb) * 3;                    // this part's slice: header + three lists of B
+      CK(cudaMemsetAsync(cls, 0, sizeof(int) * CLS_HDR, st));
+      mpcb_classify_kernel<<<(B + 255) / 256, 256, 0, st>>>(B, io.idx, io.n_idx, io.n_obs, cls);
+      CK(cudaGetLastError());
+      SolveIO io1 = io;
+      io1.idx = nullptr; io1.n_idx = nullptr;                  // the class lists carry the problem indices from here on
+      mpcb_solve_cls_kernel<<<grid + 2, SOLVE_THREADS, CLS_SMEM, st>>>(h->dt, h->dp, B, io1, cls, fb_list, fb_count);
+      h->launches++;
     }
     CK(cudaGetLastError());
     if (timed) CK(record_event(h->ev_mid, st));

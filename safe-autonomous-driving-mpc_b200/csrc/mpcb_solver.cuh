@@ -79,11 +79,17 @@ template <int S> struct ColSel<false, S> { typedef LCol type; };
 //   bit 2  hio      [18] obstacle-row bounds             bit 6  H          [55]
 //   bit 3  D, O     [20+20] lane sensitivities           bit 7  lane_inrm, lov, blo, bhi  [8+5+5+5]
 // MASK = 0: host build, evaluation kernel, cooperative kernel (S must be 1).
-template <int S, unsigned MASK>
+// NOBS: how many obstacle slots the problems of this instantiation can have (0, 1 or 2).  The thread-per-problem first
+// pass runs one instantiation per obstacle count (the batch is partitioned by n_obs first, mpcb_api.cu): a problem
+// without obstacles walks 23 rows instead of 41 and keeps 46 instead of 100 doubles of row state, so more of its
+// working set fits in shared memory.  Rows keep their numbers; the slots k >= NOBS simply do not exist.
+template <int S, unsigned MASK, int NOBS = 2>
 struct Store {
+  static constexpr int KOBS = NOBS;
+  static constexpr int MROWS = ROW_OBS + N_OBSROW * NOBS;
   template <int BIT> using G = typename ColSel<((MASK >> BIT) & 1u) != 0, S>::type;
   static constexpr int size_of(int bit) {
-    return bit == 0 ? M_ROWS : bit == 1 ? M_ROWS : bit == 2 ? 2 * N_OBSROW : bit == 3 ? 2 * N_DO : bit == 4 ? NTRI + NV
+    return bit == 0 ? MROWS : bit == 1 ? MROWS : bit == 2 ? NOBS * N_OBSROW : bit == 3 ? 2 * N_DO : bit == 4 ? NTRI + NV
          : bit == 5 ? NV + N_LANE : bit == 6 ? NTRI : N_LANE + 3 * NH;
   }
   static constexpr int shared_doubles() {
@@ -91,9 +97,9 @@ struct Store {
     for (int b = 0; b < 8; ++b) if ((MASK >> b) & 1u) n += size_of(b);
     return n;
   }
-  static constexpr int TOTAL = 2 * M_ROWS + 2 * N_OBSROW + 2 * N_DO + NTRI + NV + NV + N_LANE + NTRI + N_LANE + 3 * NH;
+  static constexpr int TOTAL = 2 * MROWS + NOBS * N_OBSROW + 2 * N_DO + NTRI + NV + NV + N_LANE + NTRI + N_LANE + 3 * NH;
   static constexpr int SHARED = shared_doubles();
-  static constexpr int LOCAL = TOTAL - SHARED;
+  static constexpr int LOCAL = (TOTAL - SHARED) > 0 ? (TOTAL - SHARED) : 1;
   G<0> v;
   G<1> rho;
   G<2> hio;         // upper bounds of the obstacle rows (BIG: row absent or dropped)
@@ -108,7 +114,7 @@ struct Store {
       typedef decltype(c.p) P;
       if (shared) { c.p = (P)sh; sh += n * S; } else { c.p = (P)lo; lo += n; }
     };
-    take(v, MASK & 1u, M_ROWS); take(rho, MASK & 2u, M_ROWS); take(hio, MASK & 4u, 2 * N_OBSROW);
+    take(v, MASK & 1u, MROWS); take(rho, MASK & 2u, MROWS); take(hio, MASK & 4u, NOBS * N_OBSROW);
     take(D, MASK & 8u, N_DO); take(O, MASK & 8u, N_DO);
     take(L, MASK & 16u, NTRI); take(rdiag, MASK & 16u, NV);
     take(q, MASK & 32u, NV); take(lane_c, MASK & 32u, N_LANE);
@@ -344,8 +350,10 @@ MPCB_HD void for_rows(const DevParams& P, const Problem& pb, const ST& st, const
     f(ROW_V + j - 1, cum, st.lov[j - 1], BIG, RowKind<1>{});
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (j > 1) f(row_r1(k, j), Sj, -BIG, st.hio[N_OBSROW * k + (j - 2)], RowKind<2>{});
-      f(row_r2(k, j), fma(P.tgap, cum, Sj), -BIG, st.hio[N_OBSROW * k + 4 + (j - 1)], RowKind<2>{});
+      if (k < ST::KOBS) {
+        if (j > 1) f(row_r1(k, j), Sj, -BIG, st.hio[N_OBSROW * k + (j - 2)], RowKind<2>{});
+        f(row_r2(k, j), fma(P.tgap, cum, Sj), -BIG, st.hio[N_OBSROW * k + 4 + (j - 1)], RowKind<2>{});
+      }
     }
   }
 }
@@ -427,9 +435,11 @@ MPCB_HD void factor(const DevParams& P, const Policy& pl, Problem& pb, const ST&
     st.rho[ROW_V + j - 1] = step_size(ROW_V + j - 1) * P.inrm_v[j - 1];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const bool on = k < pb.n_obs;
-      if (j > 1) st.rho[row_r1(k, j)] = on ? step_size(row_r1(k, j)) * P.inrm_r1[j - 1] : 0.0;
-      st.rho[row_r2(k, j)] = on ? step_size(row_r2(k, j)) * P.inrm_r2[j - 1] : 0.0;
+      if (k < ST::KOBS) {
+        const bool on = k < pb.n_obs;
+        if (j > 1) st.rho[row_r1(k, j)] = on ? step_size(row_r1(k, j)) * P.inrm_r1[j - 1] : 0.0;
+        st.rho[row_r2(k, j)] = on ? step_size(row_r2(k, j)) * P.inrm_r2[j - 1] : 0.0;
+      }
     }
   }
   double K[NTRI];
@@ -460,8 +470,10 @@ MPCB_HD void factor(const DevParams& P, const Policy& pl, Problem& pb, const ST&
     double r1 = 0.0, r2 = 0.0;   // summed over obstacles (same coefficient vectors)
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      if (j > 1) r1 += st.rho[row_r1(k, j)];
-      r2 += st.rho[row_r2(k, j)];
+      if (k < ST::KOBS) {
+        if (j > 1) r1 += st.rho[row_r1(k, j)];
+        r2 += st.rho[row_r2(k, j)];
+      }
     }
 #pragma unroll
     for (int i = 0; i < j; ++i) {
@@ -648,7 +660,7 @@ MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const 
       if (cum_hi < -pb.x0[4] - P.feas_tol) { dead_v[j - 1] = true; pin_to_j = true; }   // v_j >= 0 out of reach
 #pragma unroll
       for (int k = 0; k < 2; ++k) {
-        if (k < pb.n_obs) {
+        if (k < ST::KOBS && k < pb.n_obs) {
           const double base = (pb.obs[k][0] + pb.obs[k][1] * (j * P.h)) - pb.x0[0] - j * P.h * pb.x0[4];
           if (s_lo > base - P.obs_safe + P.feas_tol) { dead_1[k][j - 1] = true; pin_to_jm1 = true; }   // j = 1: constant row
           if (fma(P.tgap, cum_lo, s_lo) > base - P.tgap * pb.x0[4] + P.feas_tol) { dead_2[k][j - 1] = true; pin_to_j = true; }
@@ -665,11 +677,13 @@ MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const 
     screened |= dead_v[j - 1];
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
-      const double base = (pb.obs[k][0] + pb.obs[k][1] * (j * P.h)) - pb.x0[0] - j * P.h * pb.x0[4];
-      const bool on = k < pb.n_obs;
-      if (j > 1) st.hio[N_OBSROW * k + (j - 2)] = (!on || dead_1[k][j - 1]) ? BIG : base - P.obs_safe;
-      st.hio[N_OBSROW * k + 4 + (j - 1)] = (!on || dead_2[k][j - 1]) ? BIG : base - P.tgap * pb.x0[4];
-      screened |= on && (dead_1[k][j - 1] || dead_2[k][j - 1]);
+      if (k < ST::KOBS) {
+        const double base = (pb.obs[k][0] + pb.obs[k][1] * (j * P.h)) - pb.x0[0] - j * P.h * pb.x0[4];
+        const bool on = k < pb.n_obs;
+        if (j > 1) st.hio[N_OBSROW * k + (j - 2)] = (!on || dead_1[k][j - 1]) ? BIG : base - P.obs_safe;
+        st.hio[N_OBSROW * k + 4 + (j - 1)] = (!on || dead_2[k][j - 1]) ? BIG : base - P.tgap * pb.x0[4];
+        screened |= on && (dead_1[k][j - 1] || dead_2[k][j - 1]);
+      }
     }
   }
 #pragma unroll

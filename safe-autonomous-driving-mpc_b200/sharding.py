@@ -103,3 +103,39 @@ def gather_device(U_shard, status_shard, B, group=None):
         dist.all_gather(parts, mine, group=group)
         outs.append(torch.cat([p[: h - l] for p, (l, h) in zip(parts, sizes)]))
     return outs[0].reshape(B, 5, 2), outs[1].reshape(B)
+
+
+def simulate_sharded(make_sim, B, max_steps=200000, check_every=64, group=None, device=None):
+    """Closed-loop Monte-Carlo sharded by scenario ("shards the same way by scenario"): rank g drives the
+    vehicles [g*B//G, (g+1)*B//G) to their destination on its own GPU -- ``make_sim(lo, hi)`` returns the
+    ``BatchedSimulation`` of that shard (its scenarios, its start states) -- with no exchange between ranks while the
+    vehicles drive (run_simulation's loop, trajectory_tracking.py:395-410, is per vehicle).  Afterwards the final states
+    [B,5], step counts [B] and unsolved-step counts [B] are all-gathered, so every rank returns the whole fleet's
+    result; the slowest rank's number of enqueued steps comes back with it (MAX).  Returns a dict."""
+    import torch
+    dist = _dist()
+    on = dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size(group) if on else 1
+    rank = dist.get_rank(group) if on else 0
+    lo, hi = shard_bounds(B, rank, world)
+    sim = make_sim(lo, hi)
+    enq = sim.run(max_steps=max_steps, check_every=check_every) if hi > lo else 0
+    x, steps, unsolved = sim.state() if hi > lo else (np.zeros((0, 5)), np.zeros(0, np.int32), np.zeros(0, np.int32))
+    out = dict(x=np.asarray(x, dtype=np.float64).reshape(hi - lo, 5), steps=np.asarray(steps, dtype=np.int32),
+               unsolved=np.asarray(unsolved, dtype=np.int32), enqueued=int(enq), shard=(lo, hi), sim=sim)
+    if world == 1:
+        return out
+    sizes = [shard_bounds(B, g, world) for g in range(world)]
+    pad = max(h - l for l, h in sizes)
+    full = {}
+    for key, width, dt in (("x", 5, torch.float64), ("steps", 1, torch.int32), ("unsolved", 1, torch.int32)):
+        mine = torch.zeros((pad, width), dtype=dt, device=device)
+        mine[: hi - lo] = torch.from_numpy(np.ascontiguousarray(out[key]).reshape(hi - lo, width)).to(device=device, dtype=dt)
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine, group=group)
+        full[key] = torch.cat([p[: h - l] for p, (l, h) in zip(parts, sizes)]).cpu().numpy()
+    e = torch.tensor([out["enqueued"]], dtype=torch.int64, device=device)
+    dist.all_reduce(e, op=dist.ReduceOp.MAX, group=group)
+    out.update(x=full["x"].reshape(B, 5), steps=full["steps"].reshape(B), unsolved=full["unsolved"].reshape(B),
+               enqueued=int(e.cpu()[0]))
+    return out

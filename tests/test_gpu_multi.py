@@ -20,6 +20,17 @@ def _free_port():
     return p
 
 
+def _fleet(M, n=37):
+    """A small fleet on trajectory1 with per-vehicle scenario constants and start states."""
+    rng = np.random.default_rng(5)
+    scen = [M.make_scenario(2, obs_trigger_s=float(rng.uniform(20, 60)), obs_start_s=float(rng.uniform(90, 120)),
+                            obs_end_s=250.0, tl_pos=float(rng.uniform(140, 200)), tl_stop_duration=3.0) for _ in range(n)]
+    xi = np.zeros((n, 5))
+    xi[:, 0] = rng.uniform(0, 20, n)
+    xi[:, 4] = rng.uniform(0.5, 4.0, n)
+    return scen, xi
+
+
 def _worker(rank, world, port, B, q):
     import torch
     import torch.distributed as dist
@@ -40,8 +51,11 @@ def _worker(rank, world, port, B, q):
         out = T.solve_batch(*d)
         U, st = M.sharding.gather_device(out["U"], out["status"], B)          # NCCL
         stats = M.sharding.reduce_stats(out["status"].cpu().numpy(), out["iters"].cpu().numpy(), 1.0 + rank, device=dev)
-        # closed loop sharded by scenario: every rank drives its own vehicles; nothing to exchange but the verdicts
-        q.put((rank, U.cpu().numpy(), st.cpu().numpy(), stats))
+        # closed loop sharded by scenario: every rank drives its own vehicles; nothing to exchange but the results
+        T2 = M.BatchedTracker(M.TrajectoryLoader(os.path.join(ROOT, "data", "trajectory1.npz")), device=rank)
+        scen, xi = _fleet(M)
+        r = M.sharding.simulate_sharded(lambda lo, hi: M.BatchedSimulation(T2, scen[lo:hi], x_init=xi[lo:hi]), len(scen), device=dev)
+        q.put((rank, U.cpu().numpy(), st.cpu().numpy(), stats, r["x"], r["steps"], r["unsolved"]))
     finally:
         dist.destroy_process_group()
 
@@ -71,7 +85,15 @@ def test_sharded_solve_equals_unsharded_on_gpus():
     x0, obs, n = P.monte_carlo_problems(P.RefTable.from_npz(traj), B)
     ref = T.solve_batch_host(x0, obs, n)
     hist = np.bincount(ref["status"], minlength=3)
-    for rank, U, st, stats in got:
+    T1 = M.BatchedTracker(M.TrajectoryLoader(os.path.join(ROOT, "data", "trajectory1.npz")), device=0)
+    scen, xi = _fleet(M)
+    sim = M.BatchedSimulation(T1, scen, x_init=xi)
+    sim.run()
+    x1, steps1, uns1 = sim.state()
+    assert steps1.min() > 50
+    for rank, U, st, stats, sx, ssteps, suns in got:
         assert np.array_equal(U, ref["U"]) and np.array_equal(st, ref["status"])        # bitwise: problems are independent
         assert (stats["solved"], stats["maxiter"], stats["infeasible"]) == tuple(int(v) for v in hist[:3])
         assert stats["problems"] == B and stats["ms_max"] == float(world)
+        # the sharded fleet arrives exactly like the unsharded one (small shards: both run one warp per problem)
+        assert np.array_equal(ssteps, steps1) and np.array_equal(suns, uns1) and np.array_equal(sx, x1)

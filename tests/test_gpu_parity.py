@@ -347,7 +347,8 @@ def test_first_pass_caps_do_not_change_answers(gpu_trackers, port_tables):
     for kw in (dict(thread_max_rounds=4, thread_max_segments=2, thread_fail_rounds=0),
                dict(thread_max_rounds=6, thread_max_segments=4, thread_fail_rounds=0),
                dict(thread_max_rounds=5, thread_max_segments=1, thread_fail_rounds=5)):
-        r = M.BatchedTracker(L, **kw).solve_batch_host(x0, obs, n)
+        Tv = M.BatchedTracker(L, **kw)                         # kept alive: the results are views of ITS pinned buffers
+        r = Tv.solve_batch_host(x0, obs, n)
         agree = r["status"] == ref["status"]
         assert agree.mean() > 0.999, kw
         ok = agree & (ref["status"] == 0)

@@ -1,4 +1,4 @@
-"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: batch partition, result gather and statistics reduction
+"""World-size-2 gloo tests (CPU) of the multi-GPU host logic: batch partition, result gather, statistics reduction and the closed loop sharded by scenario
 (safe-autonomous-driving-mpc_b200/sharding.py).  The per-shard "solve" is the solver source compiled for the host
 (tests/hostbuild) -- the product itself has no CPU path; what is under test here is that a sharded run returns
 bit-identical results to an unsharded one and that the reductions are right."""
@@ -51,6 +51,19 @@ def _worker(rank, world, port, B, q):
             l2, h2 = S.shard_bounds(Bg, rank, world)
             Ug, sg = S.gather_device(torch.from_numpy(full["U"][l2:h2].copy()), torch.from_numpy(full["status"][l2:h2].copy()), Bg)
             assert np.array_equal(Ug.numpy(), full["U"][:Bg]) and np.array_equal(sg.numpy(), full["status"][:Bg])
+        # closed loop sharded by scenario (the simulation object is a stand-in here: the device loop has no CPU form)
+        class FakeSim:
+            def __init__(self, lo, hi):
+                self.lo, self.hi = lo, hi
+            def run(self, max_steps, check_every):
+                return 64 * (1 + self.lo // 10)
+            def state(self):
+                idx = np.arange(self.lo, self.hi)
+                return np.outer(idx, np.ones(5)) + 0.25, (idx * 3).astype(np.int32), (idx % 2).astype(np.int32)
+        r = S.simulate_sharded(FakeSim, 33)
+        idx = np.arange(33)
+        assert np.array_equal(r["x"], np.outer(idx, np.ones(5)) + 0.25) and np.array_equal(r["steps"], idx * 3)
+        assert np.array_equal(r["unsolved"], idx % 2) and r["enqueued"] == 64 * (1 + 16 // 10) and r["shard"] == S.shard_bounds(33, rank, world)
         q.put((rank, lo, hi, full["U"], full["status"], full["obj"], stats))
     finally:
         dist.destroy_process_group()
