@@ -63,6 +63,7 @@ struct SolveIO {
   const int* idx;       // optional work list: problems idx[0 .. *n_idx - 1] instead of 0 .. B-1
   const int* n_idx;
   int accumulate;       // second pass: add this pass's iteration counts to what the first pass recorded
+  int n_total;          // problems in the batch the indices refer to (bounds of the work lists; asserted in checked builds)
 };
 
 // Final evaluation at U* (predict, cost, constraint rows in the reference's order), flags, outputs.  In the first pass a
@@ -80,7 +81,11 @@ __device__ __forceinline__ bool finalize(const DevTable& T, const DevParams& P, 
   double* __restrict__ cmin_out = io.cmin;
   unsigned long long* __restrict__ active_out = io.active;
   auto defer = [&]() {
-    if (fb_list) fb_list[atomicAdd(fb_count, 1)] = b;
+    if (fb_list) {
+      const int slot = atomicAdd(fb_count, 1);
+      MPCB_ASSERT(slot >= 0 && slot < io.n_total && b >= 0 && b < io.n_total);
+      fb_list[slot] = b;
+    }
     if (iters_out) {
       if (accumulate) { iters_out[2 * b] += so.rounds; iters_out[2 * b + 1] += so.iters; }
       else { iters_out[2 * b] = so.rounds; iters_out[2 * b + 1] = so.iters; }
@@ -222,7 +227,11 @@ mpcb_classify_kernel(int B, const int* __restrict__ idx, const int* __restrict__
     const int leader = __ffs(m) - 1;
     if ((int)lane == leader) base = atomicAdd(cls + k, __popc(m));
     base = __shfl_sync(0xffffffffu, base, leader);
-    if (c == k) cls[CLS_HDR + (size_t)k * B + base + __popc(m & ((1u << lane) - 1u))] = b;
+    if (c == k) {
+      const int slot = base + __popc(m & ((1u << lane) - 1u));
+      MPCB_ASSERT(slot >= 0 && slot < B && b >= 0 && b < B);
+      cls[CLS_HDR + (size_t)k * B + slot] = b;
+    }
   }
 }
 
@@ -233,6 +242,7 @@ __device__ __forceinline__ void solve_cls_body(const DevTable& T, const DevParam
   const int t = t0 + threadIdx.x;
   const bool live = t < n_work;
   const int b = live ? list[t] : 0;
+  MPCB_ASSERT(b >= 0 && b < io.n_total);
   Problem pb;
   if (live) {
 #pragma unroll
@@ -301,6 +311,7 @@ mpcb_coop_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
     t = __shfl_sync(0xffffffffu, t, 0);
     if (t >= n_work) break;
     const int b = idx ? idx[t] : t;
+    MPCB_ASSERT(b >= 0 && b < B);
     __syncwarp();
     if (lane < 5) ws.pb.x0[lane] = io.x0[(size_t)b * 5 + lane];
     if (lane < 4) ws.pb.obs[lane >> 1][lane & 1] = io.obs_sv[(size_t)b * 4 + lane];
@@ -709,9 +720,11 @@ static bool call_uses_coop(mpcb_handle h, int B_total) { return h->params.fast_p
 // (second-pass grid sized for the expected leftovers, so that the parts do not queue whole grids of idle CTAs behind
 // each other's first passes); otherwise the second pass gets the full persistent grid -- a closed-loop step near a stop
 // line leaves a fifth of its problems to it, not the 1.4 % of the Monte-Carlo set.
-static int launch_solve(mpcb_handle h, int B, const SolveIO& io, cudaStream_t st, int* fb, bool timed, bool use_coop,
+static int launch_solve(mpcb_handle h, int B, const SolveIO& io_in, cudaStream_t st, int* fb, bool timed, bool use_coop,
                         bool part = false) {
   const int grid = (B + SOLVE_THREADS - 1) / SOLVE_THREADS;
+  SolveIO io = io_in;
+  io.n_total = B;
   h->last_shape = (h->params.fast_pass && use_coop) ? 1 : 0;
   if (timed) CK(record_event(h->ev0, st));
   if (h->params.fast_pass) {
@@ -775,7 +788,7 @@ static SolveIO make_io(const double* x0, const double* obs_sv, const int* n_obs,
   SolveIO io;
   io.x0 = x0; io.obs_sv = obs_sv; io.n_obs = n_obs; io.U = U_out; io.Xpred = Xpred_out; io.obj = obj_out;
   io.status = status_out; io.iters = iters_out; io.cmin = cmin_out; io.active = active_out; io.u0 = u0_out;
-  io.idx = nullptr; io.n_idx = nullptr; io.accumulate = 0;
+  io.idx = nullptr; io.n_idx = nullptr; io.accumulate = 0; io.n_total = 0;
   return io;
 }
 

@@ -29,6 +29,16 @@
 #define MPCB_LDG(p) (*(p))
 #endif
 
+// Checked build (-DMPCB_CHECKED, tools/gpu_checked.py): bounds of every table segment, work-list slot and class-list
+// slot are asserted on the device.  compute-sanitizer is closed on the GPU pool this was developed on, so these asserts,
+// small cases and the comparison with the CPU oracle are the memory-safety evidence (profiles/README.md).
+#if defined(MPCB_CHECKED)
+#include <assert.h>
+#define MPCB_ASSERT(c) assert(c)
+#else
+#define MPCB_ASSERT(c) ((void)0)
+#endif
+
 namespace mpcb {
 
 constexpr int NH = 5;     // horizon
@@ -152,6 +162,7 @@ MPCB_HD int seg_index_cold(const DevTable& T, int K, double x) {
   double t = (x - T.lut_s0) * T.lut_scale;
   t = t > 0.0 ? t : 0.0;                                // also catches NaN
   t = t < (double)(T.lut_n - 1) ? t : (double)(T.lut_n - 1);
+  MPCB_ASSERT((int)t >= 0 && (int)t < T.lut_n);
   int hint = MPCB_LDG(T.lut + (int)t);
   return seg_index_hint(T.s, K, x, hint);
 }
@@ -163,6 +174,7 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
     return;
   }
   int i = hint < 1 ? 1 : (hint > T.K - 1 ? T.K - 1 : hint);
+  MPCB_ASSERT(i >= 1 && i <= T.K - 1);
   double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   double ylo[4], yhi[4];
 #if defined(__CUDA_ARCH__)
@@ -181,6 +193,7 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
   load_rows(i);
   if (!((i == T.K - 1 || x_hi >= s) && (i == 1 || x_lo < s))) {   // hint off: walk / search, then load again
     i = seg_index_hint(T.s, T.K, s, hint);
+    MPCB_ASSERT(i >= 1 && i <= T.K - 1);
     x_lo = MPCB_LDG(T.s + i - 1);
     x_hi = MPCB_LDG(T.s + i);
 #if defined(__CUDA_ARCH__)
@@ -205,6 +218,7 @@ MPCB_HD void lookup_state_hint(const DevTable& T, double s, double (&val)[4], do
 MPCB_HD void lookup_control(const DevTable& T, double s, double (&u)[2], int& hint) {
   if (s >= T.s_max) { u[0] = 0.0; u[1] = 0.0; return; }
   const int i = (hint > 0) ? seg_index_hint(T.s, T.Ku, s, hint) : (hint = seg_index_cold(T, T.Ku, s));
+  MPCB_ASSERT(i >= 1 && i <= T.Ku - 1);
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
 #if defined(__CUDA_ARCH__)
   const double inv = __ldg(T.sinv + i);

@@ -10,21 +10,29 @@
 namespace mpcb {
 
 constexpr int HS_THREADS = 64;                 // intervals per CTA
-constexpr int HS_STRIDE = 5 + 60 + 144;        // doubles staged per interval (odd-ish stride: conflict-free LDS/STS.64)
+constexpr int HS_TRI = 55;                     // packed lower triangle of the 10 x 10 state block of a Hessian block
+template <bool WANT_JAC, bool WANT_HESS> struct HsStage {
+  // doubles staged per interval: defect, Jacobian block, Hessian triangle (strides odd: conflict-free LDS/STS.64)
+  static constexpr int STRIDE = WANT_HESS ? 5 + 60 + HS_TRI + 1 : (WANT_JAC ? 65 : 5);
+};
 
-// One thread per collocation interval (chunk c, interval k).  Results are staged per thread in shared memory and
-// written out by the whole CTA so that every global store instruction covers contiguous addresses.
+// One thread per collocation interval (chunk c, interval k).  Results are staged per thread in shared memory -- of the
+// symmetric 12 x 12 Hessian block only the 55 entries of its 10 x 10 lower triangle (121 doubles per interval instead of
+// 209: three CTAs per SM instead of two) -- and written out one interval per warp: lane l writes entries l, l + 32, ...
+// of the interval's contiguous output, the mirror image and the zero rows / columns of the controls filled in on the way
+// (the offsets depend on the lane only and are computed once).
 template <bool WANT_JAC, bool WANT_HESS>
 __global__ void __launch_bounds__(HS_THREADS)
 mpcb_hs_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ PlanParams P, int n_int, int N,
                     const double* __restrict__ z, const double* __restrict__ lam, double* __restrict__ defect,
                     double* __restrict__ jac, double* __restrict__ hess) {
+  constexpr int STRIDE = HsStage<WANT_JAC, WANT_HESS>::STRIDE;
   extern __shared__ double stage[];
   const int t = threadIdx.x;
   const int first = blockIdx.x * HS_THREADS;
   const int i = first + t;
   const int nb = min(HS_THREADS, n_int - first);
-  double* my = stage + (size_t)t * HS_STRIDE;
+  double* my = stage + (size_t)t * STRIDE;
   if (i < n_int) {
     const int c = i / N, k = i - c * N;
     const double* zc = z + (size_t)c * (8 * N + 5);
@@ -33,15 +41,44 @@ mpcb_hs_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ 
     for (int q = 0; q < 5; ++q) { xk[q] = zc[5 * k + q]; xn[q] = zc[5 * (k + 1) + q]; }
     u[0] = zc[5 * (N + 1) + 2 * k];
     u[1] = zc[5 * (N + 1) + 2 * k + 1];
-    hs_interval<WANT_JAC, WANT_HESS>(T, P, xk, xn, u, WANT_HESS ? lam + (size_t)i * 5 : nullptr, my, my + 5, my + 65);
+    hs_interval<WANT_JAC, WANT_HESS, true>(T, P, xk, xn, u, WANT_HESS ? lam + (size_t)i * 5 : nullptr, my, my + 5, my + 65);
   }
   __syncthreads();
-  for (int e = t; e < nb * 5; e += HS_THREADS) defect[(size_t)first * 5 + e] = stage[(e / 5) * HS_STRIDE + e % 5];
-  if (WANT_JAC && jac)
-    for (int e = t; e < nb * 60; e += HS_THREADS) jac[(size_t)first * 60 + e] = stage[(e / 60) * HS_STRIDE + 5 + e % 60];
-  if (WANT_HESS && hess)
-    for (int e = t; e < nb * 144; e += HS_THREADS)
-      hess[(size_t)first * 144 + e] = stage[(e / 144) * HS_STRIDE + 65 + e % 144];
+  const int lane = t & 31, w = t >> 5;
+  constexpr int NW = HS_THREADS / 32;
+  // defects: the CTA's nb * 5 doubles are contiguous
+  for (int e = t; e < nb * 5; e += HS_THREADS) defect[(size_t)first * 5 + e] = stage[(e / 5) * STRIDE + e % 5];
+  if (WANT_JAC && jac) {
+    for (int q = w; q < nb; q += NW) {
+      const double* src = stage + (size_t)q * STRIDE + 5;
+      double* dst = jac + ((size_t)first + q) * 60;
+      const double a = src[lane];
+      const double b = (lane < 28) ? src[32 + lane] : 0.0;
+      dst[lane] = a;
+      if (lane < 28) dst[32 + lane] = b;
+    }
+  }
+  if (WANT_HESS && hess) {
+    // entry e = lane + 32 m of the 12 x 12 block: (r, c) = (e / 12, e % 12); source = packed triangle, or zero
+    int off[5];
+#pragma unroll
+    for (int m = 0; m < 5; ++m) {
+      const int e = lane + 32 * m, r = e / 12, c = e - 12 * r;
+      const int hi = r > c ? r : c, lo = r > c ? c : r;
+      off[m] = (e < 144 && hi < 10) ? hi * (hi + 1) / 2 + lo : -1;
+    }
+#pragma unroll 2
+    for (int q = w; q < nb; q += NW) {
+      const double* src = stage + (size_t)q * STRIDE + 65;
+      double* dst = hess + ((size_t)first + q) * 144;
+      double v[5];
+#pragma unroll
+      for (int m = 0; m < 5; ++m) v[m] = off[m] >= 0 ? src[off[m]] : 0.0;
+#pragma unroll
+      for (int m = 0; m < 5; ++m)
+        if (lane + 32 * m < 144) dst[lane + 32 * m] = v[m];
+    }
+  }
 }
 
 // One thread per node (chunk c, node k = 0..N): inequality rows, stage cost and its gradient in z layout.
@@ -145,15 +182,15 @@ int mpcb_hs_eval(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int 
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
   const int grid = (n_int + HS_THREADS - 1) / HS_THREADS;
-  const size_t smem = sizeof(double) * HS_THREADS * HS_STRIDE;
-  auto launch = [&](auto kern) -> int {
+  auto launch = [&](auto kern, size_t smem) -> int {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
     kern<<<grid, HS_THREADS, smem, st>>>(h->dt, d, n_int, N, z, lam, defect, jac, hess);
     return MPCB_OK;
   };
-  if (hess) rc = launch(mpcb_hs_eval_kernel<true, true>);       // hess implies the Jacobian intermediates
-  else if (jac) rc = launch(mpcb_hs_eval_kernel<true, false>);
-  else rc = launch(mpcb_hs_eval_kernel<false, false>);
+  const size_t per = sizeof(double) * HS_THREADS;
+  if (hess) rc = launch(mpcb_hs_eval_kernel<true, true>, per * HsStage<true, true>::STRIDE);   // hess implies the Jacobian intermediates
+  else if (jac) rc = launch(mpcb_hs_eval_kernel<true, false>, per * HsStage<true, false>::STRIDE);
+  else rc = launch(mpcb_hs_eval_kernel<false, false>, per * HsStage<false, false>::STRIDE);
   if (rc != MPCB_OK) return rc;
   CK(cudaGetLastError());
   h->launches++;

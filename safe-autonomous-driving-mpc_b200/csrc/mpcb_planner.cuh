@@ -137,7 +137,10 @@ MPCB_HD void hs_hess_acc(const HsPoint& p, const double (&w)[5], double (&W)[5][
 
 // One collocation interval.  lam may be null when hess is not wanted.
 //   defect[5], jac[5][12] (columns: x_k(5), x_{k+1}(5), u_k(2)), hess[12][12] of lam . defect
-template <bool WANT_JAC, bool WANT_HESS>
+//   HESS_TRI: hess receives only the 55 entries of the lower triangle of the 10 x 10 state block, packed row by row
+//   (entry (i, j), j <= i, at i (i + 1) / 2 + j); the controls enter the defect linearly, so rows and columns 10, 11 of
+//   the 12 x 12 block are zero and the block is symmetric -- the kernel expands it while writing it out.
+template <bool WANT_JAC, bool WANT_HESS, bool HESS_TRI = false>
 MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&xk)[5], const double (&xn)[5],
                          const double (&u)[2], const double* lam, double* defect, double* jac, double* hess) {
   const double dt = P.dt, sg = P.sigma;
@@ -222,7 +225,7 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
     for (int i = 0; i < 12; ++i)
 #pragma unroll
       for (int j = 0; j < 12; ++j) {
-        if (i >= 10 || j >= 10) { hess[i * 12 + j] = 0.0; continue; }
+        if (i >= 10 || j >= 10) { if (!HESS_TRI) hess[i * 12 + j] = 0.0; continue; }
         if (j > i) continue;   // lower triangle first
         double a = 0.0;
 #pragma unroll
@@ -234,6 +237,7 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
         if (i < 5 && j < 5) direct = Wk[i][j];
         if (i >= 5 && j >= 5) direct = Wn[i - 5][j - 5];
         const double val = cf * (direct + 4.0 * a);
+        if (HESS_TRI) { hess[i * (i + 1) / 2 + j] = val; continue; }
         hess[i * 12 + j] = val;
         hess[j * 12 + i] = val;
       }
