@@ -31,7 +31,7 @@
 
 // Checked build (-DMPCB_CHECKED, tools/gpu_checked.py): bounds of every table segment, work-list slot and class-list
 // slot are asserted on the device.  compute-sanitizer is closed on the GPU pool this was developed on, so these asserts,
-// small cases and the comparison with the CPU oracle are the memory-safety evidence (profiles/README.md).
+// small cases and the parity tests are the memory-safety evidence (profiles/README.md).
 #if defined(MPCB_CHECKED)
 #include <assert.h>
 #define MPCB_ASSERT(c) assert(c)
