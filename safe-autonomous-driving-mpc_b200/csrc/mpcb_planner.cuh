@@ -31,9 +31,12 @@ struct PlanParams {
   double s_total;
 };
 
-// interp_k(s): value and slope of the bracketing segment (no s >= s_max clamp: this is the raw interpolator)
-MPCB_HD void lookup_kref(const DevTable& T, double s, double& kap, double& dkap) {
-  const int i = seg_index_cold(T, T.K, s);
+// interp_k(s): value and slope of the bracketing segment (no s >= s_max clamp: this is the raw interpolator).
+// hint: segment of a nearby point looked up before (0: none) -- the three points of a collocation interval lie within a
+// knot or two of each other, so the second and third lookups walk from the first one's segment instead of going through
+// the bucket index again (same segment either way: the walk ends on the searchsorted-left bracket).
+MPCB_HD void lookup_kref(const DevTable& T, double s, double& kap, double& dkap, int& hint) {
+  const int i = (hint > 0) ? seg_index_hint(T.s, T.K, s, hint) : (hint = seg_index_cold(T, T.K, s));
   const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
   const double y_lo = MPCB_LDG(T.y + 4 * (i - 1) + 2), y_hi = MPCB_LDG(T.y + 4 * i + 2);
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
@@ -49,14 +52,13 @@ struct HsPoint {
   bool clamped;
 };
 
-MPCB_HD void hs_point(const DevTable& T, const double (&x)[5], const double (&u)[2], HsPoint& p) {
+MPCB_HD void hs_point(const DevTable& T, const double (&x)[5], const double (&u)[2], HsPoint& p, int& hint) {
   const double s = x[0], d = x[1], o = x[2], k = x[3], v = x[4];
-  lookup_kref(T, s, p.kap, p.dkap);
+  lookup_kref(T, s, p.kap, p.dkap, hint);
   double den = 1.0 - d * p.kap;
   p.clamped = fabs(den) < 1e-4;
   if (p.clamped) den = (den != 0.0) ? ((den > 0.0) ? 1e-4 : -1e-4) : 1e-4;       // :74-77
-  p.c = cos(o);
-  p.sn = sin(o);
+  sincos(o, &p.sn, &p.c);          // one argument reduction for both
   p.g = 1.0 / den;
   p.d = d; p.k = k; p.v = v;
   const double sdot = (v * p.c) / den;
@@ -67,6 +69,18 @@ MPCB_HD void hs_point(const DevTable& T, const double (&x)[5], const double (&u)
   p.f[4] = u[1];
   p.gs = p.clamped ? 0.0 : d * p.dkap * p.g * p.g;
   p.gd = p.clamped ? 0.0 : p.kap * p.g * p.g;
+}
+
+// Structural zeros, known at compile time (the loops below are fully unrolled, so a masked term costs nothing; a
+// multiplication by a stored 0.0 would -- IEEE arithmetic does not let the compiler drop it):
+//   F = df/dx          rows s', d', o' only; s' does not depend on k, d' only on o and v
+//   M = dx_m/dx_{k,n}  = I/2 +- dt/8 F: F's pattern plus the diagonal
+//   W = sum_c w_c Hess(f_c): the block over (s, d, o, v) without (v, v), plus the (k, v) pair
+// 332 instead of 775 multiply-adds in the three matrix products of an interval.
+__host__ __device__ constexpr bool hs_fnz(int r, int c) { return r == 0 ? (c != 3) : (r == 1 ? (c == 2 || c == 4) : r == 2); }
+__host__ __device__ constexpr bool hs_mnz(int r, int c) { return r == c || hs_fnz(r, c); }
+__host__ __device__ constexpr bool hs_wnz(int r, int c) {
+  return (r == 3 || c == 3) ? ((r == 3 && c == 4) || (r == 4 && c == 3)) : !(r == 4 && c == 4);
 }
 
 // F = d f / d x (5x5; rows 3,4 are zero), variables ordered s,d,o,k,v
@@ -119,7 +133,8 @@ MPCB_HD void hs_hess_acc(const HsPoint& p, const double (&w)[5], double (&W)[5][
 #pragma unroll
   for (int r = 0; r < 5; ++r)
 #pragma unroll
-    for (int c = 0; c < 5; ++c) W[r][c] = fma(a0, H0[r][c], W[r][c]);
+    for (int c = 0; c < 5; ++c)
+      if (hs_wnz(r, c) && r != 3 && c != 3) W[r][c] = fma(a0, H0[r][c], W[r][c]);
   // f1 = v sin o
   W[2][2] = fma(w[1], -Bq, W[2][2]);
   W[2][4] = fma(w[1], p.c, W[2][4]);
@@ -128,6 +143,7 @@ MPCB_HD void hs_hess_acc(const HsPoint& p, const double (&w)[5], double (&W)[5][
   const double t = -w[2] * p.dkap;
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
+    if (c == 3) continue;                       // grad f0 has no k component
     W[0][c] = fma(t, g0[c], W[0][c]);
     W[c][0] = fma(t, g0[c], W[c][0]);
   }
@@ -145,12 +161,13 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
                          const double (&u)[2], const double* lam, double* defect, double* jac, double* hess) {
   const double dt = P.dt, sg = P.sigma;
   HsPoint pk, pn, pm;
-  hs_point(T, xk, u, pk);
-  hs_point(T, xn, u, pn);
+  int hint = 0;
+  hs_point(T, xk, u, pk, hint);
+  hs_point(T, xn, u, pn, hint);
   double xm[5];
 #pragma unroll
   for (int c = 0; c < 5; ++c) xm[c] = 0.5 * (xk[c] + xn[c]) + (dt / 8.0) * (pk.f[c] - pn.f[c]);     // :195
-  hs_point(T, xm, u, pm);
+  hs_point(T, xm, u, pm, hint);
 #pragma unroll
   for (int c = 0; c < 5; ++c) {
     const double simpson = (dt / 6.0) * (pk.f[c] + 4 * pm.f[c] + pn.f[c]);
@@ -167,8 +184,13 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
   for (int r = 0; r < 5; ++r)
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
-      Mk[r][c] = ((r == c) ? 0.5 : 0.0) + (dt / 8.0) * Fk[r][c];
-      Mn[r][c] = ((r == c) ? 0.5 : 0.0) - (dt / 8.0) * Fn[r][c];
+      if (hs_fnz(r, c)) {
+        Mk[r][c] = ((r == c) ? 0.5 : 0.0) + (dt / 8.0) * Fk[r][c];
+        Mn[r][c] = ((r == c) ? 0.5 : 0.0) - (dt / 8.0) * Fn[r][c];
+      } else {
+        Mk[r][c] = (r == c) ? 0.5 : 0.0;
+        Mn[r][c] = (r == c) ? 0.5 : 0.0;
+      }
     }
   const double cf = -sg * dt / 6.0;
   if (WANT_JAC) {
@@ -178,7 +200,8 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
       for (int c = 0; c < 5; ++c) {
         double fk = 0.0, fn = 0.0;
 #pragma unroll
-        for (int m = 0; m < 5; ++m) { fk = fma(Fm[r][m], Mk[m][c], fk); fn = fma(Fm[r][m], Mn[m][c], fn); }
+        for (int m = 0; m < 5; ++m)
+          if (hs_fnz(r, m) && hs_mnz(m, c)) { fk = fma(Fm[r][m], Mk[m][c], fk); fn = fma(Fm[r][m], Mn[m][c], fn); }
         jac[r * 12 + c] = ((r == c) ? -1.0 : 0.0) + cf * (Fk[r][c] + 4.0 * fk);
         jac[r * 12 + 5 + c] = ((r == c) ? 1.0 : 0.0) + cf * (Fn[r][c] + 4.0 * fn);
       }
@@ -218,7 +241,8 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
       for (int c = 0; c < 5; ++c) {
         double a = 0.0, b = 0.0;
 #pragma unroll
-        for (int m = 0; m < 5; ++m) { a = fma(Wm[r][m], Mk[m][c], a); b = fma(Wm[r][m], Mn[m][c], b); }
+        for (int m = 0; m < 5; ++m)
+          if (hs_wnz(r, m) && hs_mnz(m, c)) { a = fma(Wm[r][m], Mk[m][c], a); b = fma(Wm[r][m], Mn[m][c], b); }
         Tm[r][c] = a; Tm[r][5 + c] = b;
       }
 #pragma unroll
@@ -230,6 +254,7 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
         double a = 0.0;
 #pragma unroll
         for (int m = 0; m < 5; ++m) {
+          if (!hs_mnz(m, i < 5 ? i : i - 5)) continue;
           const double mi = (i < 5) ? Mk[m][i] : Mn[m][i - 5];
           a = fma(mi, Tm[m][j], a);
         }

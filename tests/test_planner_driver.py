@@ -85,8 +85,9 @@ def test_gpu_evaluator_drives_the_same_solution(gpu_trackers, port_tables):
         lambda n, st: Q.OracleEvaluator(port_tables[1], n, simpson_sign=+1, s_total=st, v_max=v_max), s_total, v_max)
     assert all(D.reference_trajectory_verdicts(Xg, Ug, Sg, s_total).values())
     # SLSQP stops at ftol = 1e-4 (the reference's setting), so rounding-level differences between the two evaluators move
-    # the accepted iterates a little; the trajectories agree to centimetres and the chunk costs to 1e-3
+    # the accepted iterates a little; the trajectories agree to centimetres and the chunk costs to 2e-3 (measured: one
+    # chunk 1.4e-3 apart once the device code took sin and cos from one sincos call, 1 ulp from the separate calls)
     assert Xg.shape == Xc.shape and np.abs(Xg - Xc).max() <= 5e-2 and np.abs(Ug - Uc).max() <= 5e-2
     assert len(logg) == len(logc)
     for a, b in zip(logg, logc):
-        assert a["N"] == b["N"] and abs(a["cost"] - b["cost"]) <= 1e-3 * max(1.0, abs(b["cost"]))
+        assert a["N"] == b["N"] and abs(a["cost"] - b["cost"]) <= 2e-3 * max(1.0, abs(b["cost"]))
