@@ -32,13 +32,49 @@ struct PlanParams {
 };
 
 // interp_k(s): value and slope of the bracketing segment (no s >= s_max clamp: this is the raw interpolator).
-// hint: segment of a nearby point looked up before (0: none) -- the three points of a collocation interval lie within a
-// knot or two of each other, so the second and third lookups walk from the first one's segment instead of going through
-// the bucket index again (same segment either way: the walk ends on the searchsorted-left bracket).
+// A lookup is a chain of dependent memory round trips (bucket index -> knots -> rows), and with one or two warps per
+// scheduler nobody hides them.  So: the five knots around a first guess and their curvatures are loaded at once and the
+// bracketing segment is picked in registers -- the bucket index is at most a knot or two off, and the three points of a
+// collocation interval lie within a knot or two of each other (hint: segment of such a neighbour, 0: none).  Two round
+// trips without a hint, one with; the walk of seg_index_hint remains as the fallback when the point is outside the
+// window.  Same segment either way: the searchsorted-left bracket clipped to [1, K - 1].
 MPCB_HD void lookup_kref(const DevTable& T, double s, double& kap, double& dkap, int& hint) {
-  const int i = (hint > 0) ? seg_index_hint(T.s, T.K, s, hint) : (hint = seg_index_cold(T, T.K, s));
-  const double x_lo = MPCB_LDG(T.s + i - 1), x_hi = MPCB_LDG(T.s + i);
-  const double y_lo = MPCB_LDG(T.y + 4 * (i - 1) + 2), y_hi = MPCB_LDG(T.y + 4 * i + 2);
+  const int K = T.K;
+  int c = hint;
+  if (c <= 0) {
+    if (T.lut) {
+      double t = (s - T.lut_s0) * T.lut_scale;
+      t = t > 0.0 ? t : 0.0;                                // also catches NaN
+      t = t < (double)(T.lut_n - 1) ? t : (double)(T.lut_n - 1);
+      c = MPCB_LDG(T.lut + (int)t);
+    } else {
+      c = seg_index(T.s, K, s);
+    }
+  }
+  c = c < 1 ? 1 : (c > K - 1 ? K - 1 : c);
+  double sw[5], kw[5];
+#pragma unroll
+  for (int j = 0; j < 5; ++j) {
+    int q = c - 2 + j;
+    q = q < 0 ? 0 : (q > K - 1 ? K - 1 : q);
+    sw[j] = MPCB_LDG(T.s + q);
+    kw[j] = MPCB_LDG(T.y + 4 * q + 2);
+  }
+  int i = -1;
+  double x_lo = 0.0, x_hi = 1.0, y_lo = 0.0, y_hi = 0.0;
+#pragma unroll
+  for (int j = 4; j >= 1; --j) {                            // candidates c - 1 .. c + 2; the lowest match wins
+    const int cand = c - 2 + j;
+    const bool ok = cand >= 1 && cand <= K - 1 && (cand == 1 || sw[j - 1] < s) && (cand == K - 1 || sw[j] >= s);
+    if (ok) { i = cand; x_lo = sw[j - 1]; x_hi = sw[j]; y_lo = kw[j - 1]; y_hi = kw[j]; }
+  }
+  if (i < 0) {                                              // outside the window: walk / search, then load
+    int h = c;
+    i = seg_index_hint(T.s, K, s, h);
+    x_lo = MPCB_LDG(T.s + i - 1); x_hi = MPCB_LDG(T.s + i);
+    y_lo = MPCB_LDG(T.y + 4 * (i - 1) + 2); y_hi = MPCB_LDG(T.y + 4 * i + 2);
+  }
+  hint = i;
   const double wl = (s - x_lo) / (x_hi - x_lo), wr = (x_hi - s) / (x_hi - x_lo);
   kap = wl * y_hi + wr * y_lo;
   dkap = (y_hi - y_lo) / (x_hi - x_lo);
@@ -161,9 +197,9 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
                          const double (&u)[2], const double* lam, double* defect, double* jac, double* hess) {
   const double dt = P.dt, sg = P.sigma;
   HsPoint pk, pn, pm;
-  int hint = 0;
-  hs_point(T, xk, u, pk, hint);
-  hs_point(T, xn, u, pn, hint);
+  int hint = 0, hint_n = 0;            // the end points look their segments up independently (in parallel), the
+  hs_point(T, xk, u, pk, hint);        // midpoint starts from the first one's
+  hs_point(T, xn, u, pn, hint_n);
   double xm[5];
 #pragma unroll
   for (int c = 0; c < 5; ++c) xm[c] = 0.5 * (xk[c] + xn[c]) + (dt / 8.0) * (pk.f[c] - pn.f[c]);     // :195
