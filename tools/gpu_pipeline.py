@@ -37,5 +37,6 @@ for side in (0,):
             return e0.elapsed_time(e1) / nsteps
         run(8)
         ms = [run(K) for _ in range(3)]
+        print("   last call per handle (first pass ms, robust pass ms, leftovers):", [tuple(round(v, 3) for v in T.last_pass_ms()) for T in Ts], flush=True)
         print(f"handles {ns}: {min(ms):.4f} ms/batch  {B / min(ms) / 1e3:.1f} M solves/s   (runs {['%.4f' % m for m in ms]})", flush=True)
         del Ts
