@@ -124,6 +124,7 @@ int mpcb_destroy(mpcb_handle h);
  *   cmin_out [B]        min over constraints_wrapper(U*) rows (reference order and sign)
  *   active_out [B]      bit r (r < 5*(7+n_obs)) set when constraint row r <= feas_tol; bit 45+i set when
  *                       variable i sits on a bound (within feas_tol)
+ * U_out and Xpred_out must be 16-byte aligned (any cudaMalloc / torch allocation is); MPCB_ERR_INVALID otherwise.
  * Replaces TrajectoryTracker.solve (trajectory_tracking.py:213-263) for a batch. */
 int mpcb_solve_batch(mpcb_handle h, int B, const double* x0, const double* obs_sv, const int* n_obs,
                      double* U_out, double* Xpred_out, double* obj_out, int* status_out, int* iters_out,

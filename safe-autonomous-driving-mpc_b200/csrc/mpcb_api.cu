@@ -147,14 +147,18 @@ __device__ __forceinline__ bool finalize(const DevTable& T, const DevParams& P, 
     status = MPCB_INFEASIBLE;
   }
 
+  // a problem's rows are 80 and 240 contiguous bytes, 16-byte aligned: 128-bit stores (the problems of a CTA are not
+  // neighbours in the batch once it is partitioned by obstacle count, so there is nothing to coalesce across threads)
+  {
+    double2* u2 = reinterpret_cast<double2*>(U_out + (size_t)b * NV);
 #pragma unroll
-  for (int i = 0; i < NV; ++i) U_out[(size_t)b * NV + i] = pb.U[i];
-  if (io.u0) { io.u0[(size_t)b * 2] = pb.U[0]; io.u0[(size_t)b * 2 + 1] = pb.U[1]; }
+    for (int i = 0; i < NV / 2; ++i) u2[i] = make_double2(pb.U[2 * i], pb.U[2 * i + 1]);
+  }
+  if (io.u0) *reinterpret_cast<double2*>(io.u0 + (size_t)b * 2) = make_double2(pb.U[0], pb.U[1]);
   if (Xpred_out) {
+    double2* x2 = reinterpret_cast<double2*>(Xpred_out + (size_t)b * 30);
 #pragma unroll
-    for (int j = 0; j <= NH; ++j)
-#pragma unroll
-      for (int c = 0; c < 5; ++c) Xpred_out[(size_t)b * 30 + 5 * j + c] = X[j][c];
+    for (int e = 0; e < 15; ++e) x2[e] = make_double2(X[(2 * e) / 5][(2 * e) % 5], X[(2 * e + 1) / 5][(2 * e + 1) % 5]);
   }
   if (obj_out) obj_out[b] = cost;
   if (status_out) status_out[b] = status;
@@ -796,6 +800,7 @@ int mpcb_solve_batch(mpcb_handle h, int B, const double* x0, const double* obs_s
                      double* Xpred_out, double* obj_out, int* status_out, int* iters_out, double* cmin_out,
                      unsigned long long* active_out, void* cuda_stream) {
   if (!h || B < 0 || (B > 0 && (!x0 || !obs_sv || !n_obs || !U_out))) return MPCB_ERR_INVALID;
+  if ((((size_t)U_out) | ((size_t)Xpred_out)) & 15u) return MPCB_ERR_INVALID;      // rows are written with 128-bit stores
   if (B == 0) return MPCB_OK;
   CK(cudaSetDevice(h->device));
   int rc = ensure_fb(h, B);
