@@ -9,18 +9,20 @@
 
 namespace mpcb {
 
-constexpr int HS_THREADS = 64;                 // intervals per CTA
+constexpr int HS_THREADS = 64;                 // threads per CTA: two lanes per collocation interval (32 / 96 / 128: the same
+                                               // 38.9 - 40.4 us on the x64 tile)
+constexpr int HS_INTERVALS = HS_THREADS / 2;   // intervals per CTA
 constexpr int HS_TRI = 55;                     // packed lower triangle of the 10 x 10 state block of a Hessian block
 template <bool WANT_JAC, bool WANT_HESS> struct HsStage {
   // doubles staged per interval: defect, Jacobian block, Hessian triangle (strides odd: conflict-free LDS/STS.64)
   static constexpr int STRIDE = WANT_HESS ? 5 + 60 + HS_TRI + 1 : (WANT_JAC ? 65 : 5);
 };
 
-// One thread per collocation interval (chunk c, interval k).  Results are staged per thread in shared memory -- of the
-// symmetric 12 x 12 Hessian block only the 55 entries of its 10 x 10 lower triangle (121 doubles per interval instead of
-// 209: three CTAs per SM instead of two) -- and written out one interval per warp: lane l writes entries l, l + 32, ...
-// of the interval's contiguous output, the mirror image and the zero rows / columns of the controls filled in on the way
-// (the offsets depend on the lane only and are computed once).
+// Two lanes per collocation interval (chunk c, interval k): hs_interval_pair of mpcb_planner.cuh.  Results are staged per
+// interval in shared memory -- of the symmetric 12 x 12 Hessian block only the 55 entries of its 10 x 10 lower triangle
+// (121 doubles per interval) -- and written out one interval per warp: lane l writes entries l, l + 32, ... of the
+// interval's contiguous output, the mirror image and the zero rows / columns of the controls filled in on the way (the
+// offsets depend on the lane only and are computed once).
 template <bool WANT_JAC, bool WANT_HESS>
 __global__ void __launch_bounds__(HS_THREADS)
 mpcb_hs_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ PlanParams P, int n_int, int N,
@@ -29,10 +31,11 @@ mpcb_hs_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ 
   constexpr int STRIDE = HsStage<WANT_JAC, WANT_HESS>::STRIDE;
   extern __shared__ double stage[];
   const int t = threadIdx.x;
-  const int first = blockIdx.x * HS_THREADS;
-  const int i = first + t;
-  const int nb = min(HS_THREADS, n_int - first);
-  double* my = stage + (size_t)t * STRIDE;
+  const int first = blockIdx.x * HS_INTERVALS;
+  const int q0 = t >> 1, p = t & 1;
+  const int i = first + q0;
+  const int nb = min(HS_INTERVALS, n_int - first);
+  const unsigned pair_mask = __ballot_sync(0xffffffffu, i < n_int);
   if (i < n_int) {
     const int c = i / N, k = i - c * N;
     const double* zc = z + (size_t)c * (8 * N + 5);
@@ -41,7 +44,8 @@ mpcb_hs_eval_kernel(const __grid_constant__ DevTable T, const __grid_constant__ 
     for (int q = 0; q < 5; ++q) { xk[q] = zc[5 * k + q]; xn[q] = zc[5 * (k + 1) + q]; }
     u[0] = zc[5 * (N + 1) + 2 * k];
     u[1] = zc[5 * (N + 1) + 2 * k + 1];
-    hs_interval<WANT_JAC, WANT_HESS, true>(T, P, xk, xn, u, WANT_HESS ? lam + (size_t)i * 5 : nullptr, my, my + 5, my + 65);
+    hs_interval_pair<WANT_JAC, WANT_HESS>(T, P, xk, xn, u, WANT_HESS ? lam + (size_t)i * 5 : nullptr, p, pair_mask,
+                                          stage + (size_t)q0 * STRIDE);
   }
   __syncthreads();
   const int lane = t & 31, w = t >> 5;
@@ -181,13 +185,13 @@ int mpcb_hs_eval(mpcb_handle h, const mpcb_planner_params* p, int n_chunks, int 
   const int n_int = (int)n_int_ll;
   CK(cudaSetDevice(h->device));
   cudaStream_t st = (cudaStream_t)cuda_stream;
-  const int grid = (n_int + HS_THREADS - 1) / HS_THREADS;
+  const int grid = (n_int + HS_INTERVALS - 1) / HS_INTERVALS;
   auto launch = [&](auto kern, size_t smem) -> int {
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));   // per device
     kern<<<grid, HS_THREADS, smem, st>>>(h->dt, d, n_int, N, z, lam, defect, jac, hess);
     return MPCB_OK;
   };
-  const size_t per = sizeof(double) * HS_THREADS;
+  const size_t per = sizeof(double) * HS_INTERVALS;
   if (hess) rc = launch(mpcb_hs_eval_kernel<true, true>, per * HsStage<true, true>::STRIDE);   // hess implies the Jacobian intermediates
   else if (jac) rc = launch(mpcb_hs_eval_kernel<true, false>, per * HsStage<true, false>::STRIDE);
   else rc = launch(mpcb_hs_eval_kernel<false, false>, per * HsStage<false, false>::STRIDE);

@@ -305,6 +305,152 @@ MPCB_HD void hs_interval(const DevTable& T, const PlanParams& P, const double (&
   }
 }
 
+#if defined(__CUDACC__)
+// The same interval evaluated by TWO lanes (lane pair p = 0 / 1 of a warp, partner = lane ^ 1): what the GPU kernel runs.
+// Lane p owns the end point x_k (p = 0) resp. x_{k+1} (p = 1): its dynamics, Jacobian F_p, M_p = dx_m/dx_p, the weighted
+// Hessian W_p and T_p = W_m M_p; the midpoint (which needs both ends' dynamics: three doubles cross the pair) is
+// evaluated by both.  Both lanes run ONE instruction stream on mirrored data:
+//   Jacobian   lane p writes the five columns of its own state
+//   Hessian    lane p writes the triangle of its own diagonal block, cf (W_p + 4 M_p' T_p), and half of the cross block
+//              4 cf M_n' W_m M_k: with C_p[a][b] = sum_m M_partner[m][a] T_p[m][b], lane 0 holds H_nk[a][b] and lane 1
+//              H_nk[b][a], so each takes the entries a <= b (lane 0 keeps the diagonal); M's 13 structural nonzeros
+//              are what the lanes exchange.
+// 170 multiply-adds per lane in the matrix products instead of 332 in one thread, about half the registers, and twice
+// the warps per SM.  slot: the interval's staging area (defect 5, Jacobian 60 at +5, Hessian triangle 55 at +65).
+// pair_mask: the lanes of the warp that are inside hs_interval_pair (whole pairs).
+__device__ __forceinline__ double hs_xchg(unsigned mask, double v) { return __shfl_xor_sync(mask, v, 1); }
+
+template <bool WANT_JAC, bool WANT_HESS>
+__device__ __forceinline__ void hs_interval_pair(const DevTable& T, const PlanParams& P, const double (&xk)[5],
+                                                 const double (&xn)[5], const double (&u)[2], const double* lam, int p,
+                                                 unsigned pair_mask, double* slot) {
+  const double dt = P.dt, sg = P.sigma;
+  const double sgn = p ? -1.0 : 1.0;
+  double xo[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) xo[c] = p ? xn[c] : xk[c];
+  HsPoint po, pm;
+  int hint = 0;
+  hs_point(T, xo, u, po, hint);
+  double fk[5], fn[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) {
+    const double other = (c < 3) ? hs_xchg(pair_mask, po.f[c]) : u[c - 3];
+    fk[c] = p ? other : po.f[c];
+    fn[c] = p ? po.f[c] : other;
+  }
+  double xm[5];
+#pragma unroll
+  for (int c = 0; c < 5; ++c) xm[c] = 0.5 * (xk[c] + xn[c]) + (dt / 8.0) * (fk[c] - fn[c]);        // :195
+  hs_point(T, xm, u, pm, hint);
+  if (p == 0) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      const double simpson = (dt / 6.0) * (fk[c] + 4 * pm.f[c] + fn[c]);
+      const double x_pred = (sg < 0.0) ? (xk[c] - simpson) : (xk[c] + simpson);                     // :198 / C7
+      slot[c] = xn[c] - x_pred;                                                                     // :200
+    }
+  }
+  if (!WANT_JAC && !WANT_HESS) return;
+  double Fo[5][5], Fm[5][5];
+  hs_jac(po, Fo);
+  hs_jac(pm, Fm);
+  double Mo[5][5];            // d x_m / d x_own
+#pragma unroll
+  for (int r = 0; r < 5; ++r)
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      if (hs_fnz(r, c)) Mo[r][c] = ((r == c) ? 0.5 : 0.0) + sgn * ((dt / 8.0) * Fo[r][c]);
+      else Mo[r][c] = (r == c) ? 0.5 : 0.0;
+    }
+  const double cf = -sg * dt / 6.0;
+  if (WANT_JAC) {
+    double* jac = slot + 5;
+    const int col0 = 5 * p;
+#pragma unroll
+    for (int r = 0; r < 5; ++r) {
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        double fo = 0.0;
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+          if (hs_fnz(r, m) && hs_mnz(m, c)) fo = fma(Fm[r][m], Mo[m][c], fo);
+        jac[r * 12 + col0 + c] = ((r == c) ? -sgn : 0.0) + cf * (Fo[r][c] + 4.0 * fo);
+      }
+      if (p == 0) {             // u enters f additively (rows 3, 4) and cancels in x_m: d defect / d u = -sigma dt B
+        jac[r * 12 + 10] = (r == 3) ? 6.0 * cf : 0.0;
+        jac[r * 12 + 11] = (r == 4) ? 6.0 * cf : 0.0;
+      }
+    }
+  }
+  if (WANT_HESS) {
+    double* tri_out = slot + 65;
+    double l[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) l[c] = lam[c];
+    double gm[5];   // grad_x (lam . f)(x_m) = Fm' lam
+#pragma unroll
+    for (int c = 0; c < 5; ++c) {
+      double a = 0.0;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) a = fma(Fm[r][c], l[r], a);
+      gm[c] = a;
+    }
+    double Wm[5][5], Wo[5][5];
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) { Wm[r][c] = 0.0; Wo[r][c] = 0.0; }
+    hs_hess_acc(pm, l, Wm);
+    double wo[5];
+#pragma unroll
+    for (int c = 0; c < 5; ++c) wo[c] = l[c] + sgn * (0.5 * dt * gm[c]);
+    hs_hess_acc(po, wo, Wo);
+    double To[5][5];          // W_m M_own
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) {
+        double a = 0.0;
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+          if (hs_wnz(r, m) && hs_mnz(m, c)) a = fma(Wm[r][m], Mo[m][c], a);
+        To[r][c] = a;
+      }
+    double Mx[5][5];          // the partner's M (its structural nonzeros cross the pair)
+#pragma unroll
+    for (int r = 0; r < 5; ++r)
+#pragma unroll
+      for (int c = 0; c < 5; ++c) Mx[r][c] = hs_mnz(r, c) ? hs_xchg(pair_mask, Mo[r][c]) : 0.0;
+    // own diagonal block: rows / columns 5 p + (0..4)
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j <= i; ++j) {
+        double a = 0.0;
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+          if (hs_mnz(m, i)) a = fma(Mo[m][i], To[m][j], a);
+        const double val = cf * (Wo[i][j] + 4.0 * a);
+        tri_out[p ? ((5 + i) * (6 + i) / 2 + 5 + j) : (i * (i + 1) / 2 + j)] = val;
+      }
+    // cross block, entries a <= b of C[a][b] = sum_m Mx[m][a] To[m][b]: lane 0 -> H(5 + a, b), lane 1 -> H(5 + b, a)
+#pragma unroll
+    for (int a = 0; a < 5; ++a)
+#pragma unroll
+      for (int b = a; b < 5; ++b) {
+        double acc = 0.0;
+#pragma unroll
+        for (int m = 0; m < 5; ++m)
+          if (hs_mnz(m, a)) acc = fma(Mx[m][a], To[m][b], acc);
+        const double val = cf * (0.0 + 4.0 * acc);
+        if (p == 0) tri_out[(5 + a) * (6 + a) / 2 + b] = val;
+        else if (a != b) tri_out[(5 + b) * (6 + b) / 2 + a] = val;
+      }
+  }
+}
+#endif
+
 // Node rows (trajectory_planning.py:249-307), 6 per node k = 0..N:
 //   (v+slack) - v_min, v_max - (v+slack), a_max - k v^2, a_max + k v^2, k - k_min, k_max - k      (slack = 0 at k = N)
 MPCB_HD void hs_node_rows(const PlanParams& P, const double (&x)[5], double slack, double vmin, double vmax,
