@@ -326,6 +326,11 @@ __device__ __forceinline__ void hs_interval_pair(const DevTable& T, const PlanPa
                                                  unsigned pair_mask, double* slot) {
   const double dt = P.dt, sg = P.sigma;
   const double sgn = p ? -1.0 : 1.0;
+  double l[5] = {0.0, 0.0, 0.0, 0.0, 0.0};      // multipliers: loaded up front, consumed a thousand instructions later
+  if (WANT_HESS) {
+#pragma unroll
+    for (int c = 0; c < 5; ++c) l[c] = MPCB_LDG(lam + c);
+  }
   double xo[5];
 #pragma unroll
   for (int c = 0; c < 5; ++c) xo[c] = p ? xn[c] : xk[c];
@@ -385,9 +390,6 @@ __device__ __forceinline__ void hs_interval_pair(const DevTable& T, const PlanPa
   }
   if (WANT_HESS) {
     double* tri_out = slot + 65;
-    double l[5];
-#pragma unroll
-    for (int c = 0; c < 5; ++c) l[c] = lam[c];
     double gm[5];   // grad_x (lam . f)(x_m) = Fm' lam
 #pragma unroll
     for (int c = 0; c < 5; ++c) {
