@@ -24,6 +24,16 @@ def make_scenario(which=2, **over):
     return s
 
 
+# Solver caps for a large fleet whose vehicles are in different phases of their drives.  The defaults are tuned for a
+# Monte-Carlo batch of perturbed states, where 1.4 % of the problems are left to the robust pass; in a closed loop a
+# quarter of the vehicles is at any time braking for, waiting at or leaving a stop line, the two-level first pass with
+# ONE active-set update per linearisation gives most of those up, and the robust pass (one warp per problem) becomes the
+# step.  Three updates per linearisation keep them in the first pass.  Measured on B200, 65,536 vehicles on trajectory3
+# with staggered starts and per-vehicle scenarios (tools/gpu_sim_fleet.py): 16.0 -> 41.8 M vehicle-steps/s; the same caps
+# cost a Monte-Carlo batch 0.31 -> 0.42+ ms in its first pass, which is why they are not the default.
+#     T = BatchedTracker(loader, **FLEET_SOLVER_CAPS);  sim = BatchedSimulation(T, scenarios, x_init=...)
+FLEET_SOLVER_CAPS = dict(thread_max_segments=3)
+
 CHECKS = ("destination", "on_road", "steering", "acceleration", "obstacle", "light", "history_complete")
 
 
