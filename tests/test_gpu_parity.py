@@ -301,6 +301,17 @@ def test_argument_errors_and_degenerate_sizes(gpu_trackers):
     xe = np.array([[L.s_max - 0.5, 0.0, 0.0, 0.0, 1.0], [L.s_max + 3.0, 0.0, 0.0, 0.0, 1.0]])
     r = T.solve_batch_host(xe, np.zeros((2, 2, 2)), np.zeros(2, dtype=np.int32))
     assert np.all(np.isfinite(r["U"])) and np.all(np.isfinite(r["obj"]))
+    # device entry point: rows are written with 128-bit stores, so U_out / Xpred_out must be 16-byte aligned
+    import torch
+    dx = torch.from_numpy(x0).cuda(); do = torch.from_numpy(obs).cuda(); dn = torch.zeros(3, dtype=torch.int32, device="cuda")
+    buf = torch.zeros(3 * 10 + 2, dtype=torch.float64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ok = lib.mpcb_solve_batch(T._h, 3, dx.data_ptr(), do.data_ptr(), dn.data_ptr(), buf.data_ptr(), None, None, None, None, None, None, C.c_void_p(st))
+    assert ok == 0
+    bad = lib.mpcb_solve_batch(T._h, 3, dx.data_ptr(), do.data_ptr(), dn.data_ptr(), buf.data_ptr() + 8, None, None, None, None, None, None, C.c_void_p(st))
+    assert bad == -1
+    torch.cuda.synchronize()
+    assert np.array_equal(buf[:30].cpu().numpy().reshape(3, 5, 2), T.solve_batch_host(x0, obs, np.zeros(3, dtype=np.int32))["U"])
     p = _lib.Params()
     lib.mpcb_default_params(C.byref(p))
     p.N = 7
