@@ -214,10 +214,19 @@ def config_extras(M, P, dev, torch):
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         _, steps, _ = sim.state()
+        sim = M.BatchedSimulation(T, scen, B=nveh, hot_start=True)      # previous plan, advanced one step, as the start
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        sim.run(max_steps=len(hu) + 64, check_every=128)
+        torch.cuda.synchronize()
+        dt_hot = time.perf_counter() - t0
+        _, steps_hot, _ = sim.state()
         out[f"config{i + 0}_trajectory{i}_closed_loop"] = {
             "steps": int(len(hu)), "status_hist": np.bincount(st, minlength=3).tolist(), "wall_s": wall,
             "solve_ms_p50": float(np.median(ht)), "solve_ms_p99": float(np.quantile(ht, 0.99)),
             "device_loop_vehicles": nveh, "device_loop_vehicle_steps_per_s": float(steps.sum() / dt),
+            "device_loop_hot_start_vehicle_steps_per_s": float(steps_hot.sum() / dt_hot),
+            "device_loop_hot_start_steps": int(steps_hot[0]),
             "reference": "trajectory_tracking.py:377-443"}
         del sim, T
     traj3 = os.path.join(ROOT, "data", "trajectory3.npz")

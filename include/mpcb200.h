@@ -254,6 +254,11 @@ int mpcb_sim_destroy(mpcb_sim_handle s);
 /* n_steps closed-loop steps, asynchronous on cuda_stream (3 + the solver's launches per step, no host round trip).
  * Vehicles that have passed s_max - 1 are frozen. */
 int mpcb_sim_step(mpcb_sim_handle s, int n_steps, void* cuda_stream);
+/* Hot start (off by default): from its second step on, a vehicle's first pass starts from its previous plan advanced by
+ * one step instead of from the reference's table-based warm start (trajectory_tracking.py:223-246), with the rows that
+ * sit on their bounds there taken as active.  The problem solved is the same and so is its converged answer; what changes
+ * is how often the robust pass is needed (a vehicle waiting at a red light poses the same problem a hundred steps in a row). */
+int mpcb_sim_set_hot_start(mpcb_sim_handle s, int on);
 /* number of vehicles still driving (synchronises the stream) */
 int mpcb_sim_alive(mpcb_sim_handle s, int* n_alive, void* cuda_stream);
 /* HOST outputs (any may be NULL): current states [B][5], steps driven [B], steps whose solve was not MPCB_SOLVED [B] */

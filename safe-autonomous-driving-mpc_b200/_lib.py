@@ -100,6 +100,7 @@ SYMBOLS = {
     "mpcb_sim_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_void_p, C.c_int, C.POINTER(Scenario), C.c_int, C.c_void_p, C.c_int]),
     "mpcb_sim_destroy": (C.c_int, [C.c_void_p]),
     "mpcb_sim_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "mpcb_sim_set_hot_start": (C.c_int, [C.c_void_p, C.c_int]),
     "mpcb_sim_alive": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.c_void_p]),
     "mpcb_sim_state": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "mpcb_sim_check": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

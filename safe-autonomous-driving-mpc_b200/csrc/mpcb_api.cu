@@ -63,6 +63,8 @@ struct SolveIO {
   const int* idx;       // optional work list: problems idx[0 .. *n_idx - 1] instead of 0 .. B-1
   const int* n_idx;
   int accumulate;       // second pass: add this pass's iteration counts to what the first pass recorded
+  const double* U_start;  // optional [B][10]: hot start of the first pass (closed loop: the previous step's plans, shifted
+  int shift_start;        // by one step when shift_start != 0); may alias U
   int n_total;          // problems in the batch the indices refer to (bounds of the work lists; asserted in checked builds)
 };
 
@@ -239,6 +241,13 @@ mpcb_classify_kernel(int B, const int* __restrict__ idx, const int* __restrict__
   }
 }
 
+// hot start of problem b: the stored plan, optionally advanced by one step (the last step is repeated)
+__device__ __forceinline__ void load_hot_start(const SolveIO& io, int b, double (&Uh)[NV]) {
+  const double* __restrict__ src = io.U_start + (size_t)b * NV;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) Uh[i] = io.shift_start ? src[i + 2 < NV ? i + 2 : i] : src[i];
+}
+
 template <int NOBS>
 __device__ __forceinline__ void solve_cls_body(const DevTable& T, const DevParams& P, const SolveIO& io, const int* __restrict__ list,
                                                int n_work, int t0, int* __restrict__ fb_list, int* __restrict__ fb_count) {
@@ -266,7 +275,10 @@ __device__ __forceinline__ void solve_cls_body(const DevTable& T, const DevParam
   extern __shared__ double solve_smem[];
   double solve_local[St::LOCAL];
   const St st(solve_smem + threadIdx.x, solve_local);
-  SolveOut so = solve_one<true>(T, P, pb, st, live);
+  double Uh[NV];
+  const bool hot = io.U_start != nullptr;             // CTA-uniform
+  if (hot && live) load_hot_start(io, b, Uh);
+  SolveOut so = solve_one<true>(T, P, pb, st, live, (hot && live) ? Uh : nullptr);
   if (!live) return;
   finalize<true>(T, P, pb, so, b, io.accumulate != 0, io, fb_list, fb_count);
 }
@@ -321,7 +333,14 @@ mpcb_coop_kernel(const __grid_constant__ DevTable T, const __grid_constant__ Dev
     if (lane < 4) ws.pb.obs[lane >> 1][lane & 1] = io.obs_sv[(size_t)b * 4 + lane];
     if (lane == 0) ws.pb.n_obs = min(max(io.n_obs[b], 0), 2);
     __syncwarp();
-    const SolveOut so = coop_solve<FIRST_PASS>(T, P, ws, lane);
+    if (FIRST_PASS && io.U_start) {
+      if (lane < NV) {
+        const double* __restrict__ src = io.U_start + (size_t)b * NV;
+        ws.hot[lane] = io.shift_start ? src[lane + 2 < NV ? lane + 2 : lane] : src[lane];
+      }
+      __syncwarp();
+    }
+    const SolveOut so = coop_solve<FIRST_PASS>(T, P, ws, lane, FIRST_PASS && io.U_start != nullptr);
     if (lane == 0) finalize<FIRST_PASS>(T, P, ws.pb, so, b, io.accumulate != 0, io, fb_list, fb_count);
     __syncwarp();
   }
@@ -446,7 +465,7 @@ int cuda_fail(cudaError_t e, const char* where) {
 
 extern "C" {
 
-int mpcb_abi_version(void) { return 6; }
+int mpcb_abi_version(void) { return 7; }
 unsigned long long mpcb_sizeof_params(void) { return sizeof(mpcb_params); }
 unsigned long long mpcb_sizeof_planner_params(void) { return sizeof(mpcb_planner_params); }
 
@@ -792,7 +811,7 @@ static SolveIO make_io(const double* x0, const double* obs_sv, const int* n_obs,
   SolveIO io;
   io.x0 = x0; io.obs_sv = obs_sv; io.n_obs = n_obs; io.U = U_out; io.Xpred = Xpred_out; io.obj = obj_out;
   io.status = status_out; io.iters = iters_out; io.cmin = cmin_out; io.active = active_out; io.u0 = u0_out;
-  io.idx = nullptr; io.n_idx = nullptr; io.accumulate = 0; io.n_total = 0;
+  io.idx = nullptr; io.n_idx = nullptr; io.accumulate = 0; io.n_total = 0; io.U_start = nullptr; io.shift_start = 0;
   return io;
 }
 
@@ -812,12 +831,14 @@ int mpcb_solve_batch(mpcb_handle h, int B, const double* x0, const double* obs_s
 // Solve the problems idx[0 .. *n_idx - 1] of a batch of B (both on the device; the closed loop's list of vehicles that
 // are still driving).  Outputs of the other problems are left untouched.
 int mpcb_solve_list_internal(mpcb_handle h, int B, const int* idx, const int* n_idx, const double* x0, const double* obs_sv,
-                             const int* n_obs, double* U_out, int* status_out, cudaStream_t st) {
+                             const int* n_obs, double* U_out, int* status_out, cudaStream_t st, const double* U_start) {
   int rc = ensure_fb(h, B);
   if (rc != MPCB_OK) return rc;
   SolveIO io = make_io(x0, obs_sv, n_obs, U_out, nullptr, nullptr, status_out, nullptr, nullptr, nullptr);
   io.idx = idx;
   io.n_idx = n_idx;
+  io.U_start = U_start;          // closed loop: the previous step's plans (U_out itself), advanced by one step
+  io.shift_start = 1;
   return launch_solve(h, B, io, st, h->fb, true, call_uses_coop(h, B));
 }
 

@@ -48,6 +48,7 @@ struct WarpShared {
   double xh[NH + 1][2];                 // linearisation: (d_j, o_j) of the nominal rollout
   double lk[NH + 1][8];                 // linearisation: reference values and slopes at s_0 .. s_5
   double ur[NH][2];                     // warm start: reference controls at the five probe positions
+  double hot[NV];                       // hot start of the first pass (mpcb_api.cu), when the caller supplies one
   double scal[4];                       // lane-0 scalars broadcast through shared memory
   int iflag[2];
 };
@@ -276,7 +277,7 @@ __device__ void coop_linearise(const DevTable& T, const DevParams& P, WarpShared
 }
 
 template <bool FIRST_PASS>
-__device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared& ws, int lane) {
+__device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared& ws, int lane, bool hot = false) {
   const unsigned FULL = 0xffffffffu;
   const Store<1, 0u> st(nullptr, ws.buf);
   Problem& pb = ws.pb;
@@ -302,7 +303,16 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
     pb.hint[lane] = hint;
   }
   __syncwarp();
-  if (lane == 0) ws.iflag[0] = prologue(T, P, pb, st, ws.ur) ? 1 : 0;
+  if (lane == 0) {
+    ws.iflag[0] = prologue(T, P, pb, st, ws.ur) ? 1 : 0;
+    if (FIRST_PASS && hot) {               // start from the supplied plan, clipped like any start (solve_one does the same)
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const double u = clipd(ws.hot[i], P.umin[i & 1], P.umax[i & 1]);
+        pb.U[i] = (i & 1) ? clipd(u, st.blo[i >> 1], st.bhi[i >> 1]) : u;
+      }
+    }
+  }
   __syncwarp();
   CPROF_T(tp1);
   CPROF_ADD(0, tp0, tp1);
@@ -397,6 +407,10 @@ __device__ SolveOut coop_solve(const DevTable& T, const DevParams& P, WarpShared
         v[k] = clipd(zt, lo[k], hi[k]);
         e[k] = pl.e_init;
         aprev[k] = false;
+        if (FIRST_PASS && hot && ex[k] && (zt <= lo[k] + P.feas_tol || zt >= hi[k] - P.feas_tol)) {
+          e[k] = pl.n_rung - 1;             // hot start: a row on its bound starts as active (two-level policy: rung "on")
+          aprev[k] = true;
+        }
       }
       first = false;
     }

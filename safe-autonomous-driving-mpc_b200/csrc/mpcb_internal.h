@@ -59,4 +59,4 @@ struct mpcb_ctx {
 // Solve the problems idx[0 .. *n_idx - 1] (device list) of a batch of B on stream st; used by the device closed loop.
 extern "C" int mpcb_solve_list_internal(mpcb_handle h, int B, const int* idx, const int* n_idx, const double* x0,
                                         const double* obs_sv, const int* n_obs, double* U_out, int* status_out,
-                                        cudaStream_t st);
+                                        cudaStream_t st, const double* U_start);

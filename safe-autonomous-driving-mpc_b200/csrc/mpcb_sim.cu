@@ -185,6 +185,7 @@ using namespace mpcb;
 struct mpcb_sim {
   mpcb_handle h;
   int B, cap, t;              // vehicles, history capacity (steps), steps recorded so far
+  int hot_start = 0;          // first pass of step t > 0 starts from step t - 1's plans advanced by one step (mpcb_sim_set_hot_start)
   double dt, s_stop;
   DevScenario* scen = nullptr;
   double *x = nullptr, *fsm_f = nullptr, *obs_sv = nullptr, *U = nullptr;
@@ -287,7 +288,8 @@ int mpcb_sim_step(mpcb_sim_handle s, int n_steps, void* cuda_stream) {
                                           s->alive_cnt + ((s->t + 1) & 1));
     CK(cudaGetLastError());
     // the solve runs over the list of vehicles still driving (arrived vehicles are frozen and cost nothing)
-    int rc = mpcb_solve_list_internal(s->h, s->B, s->alive_idx, cnt, s->x, s->obs_sv, s->n_obs, s->U, s->status, st);
+    int rc = mpcb_solve_list_internal(s->h, s->B, s->alive_idx, cnt, s->x, s->obs_sv, s->n_obs, s->U, s->status, st,
+                                      (s->hot_start && s->t > 0) ? s->U : nullptr);
     if (rc != MPCB_OK) return rc;
     mpcb_plant_kernel<<<grid, 128, 0, st>>>(s->h->dt, s->B, s->dt, s->x, s->U, s->status, s->alive, s->steps,
                                             s->n_unsolved, rec, s->hist_x, s->hist_u, s->hist_status);
@@ -295,6 +297,12 @@ int mpcb_sim_step(mpcb_sim_handle s, int n_steps, void* cuda_stream) {
     s->h->launches += 2;
     s->t += 1;
   }
+  return MPCB_OK;
+}
+
+int mpcb_sim_set_hot_start(mpcb_sim_handle s, int on) {
+  if (!s) return MPCB_ERR_INVALID;
+  s->hot_start = on ? 1 : 0;
   return MPCB_OK;
 }
 

@@ -702,14 +702,18 @@ MPCB_HD bool prologue(const DevTable& T, const DevParams& P, Problem& pb, const 
 //                      certified"), no infeasibility verdict other than the rigorous screens.
 // FIRST_PASS = false: robust ladder with OSQP's infeasibility certificate; inexact Gauss-Newton: the QP of a round is
 //                      solved only as accurately as the previous SQP step warrants (P.qp_forcing).
-// U_start (robust pass only, optional): the controls the first pass had reached when it gave the problem up; the SQP
-// continues from there instead of from the warm start (clipped to the box and to the screen's pins like any start).
+// U_start (optional): controls to start from instead of the reference's warm start (clipped to the box and to the
+// screen's pins like any start).  First pass: a HOT start -- the plan of a neighbouring problem, in the closed loop the
+// previous time step's solution shifted by one step; rows that sit on their bounds there start as active, so the first
+// segment is already a KKT solve on that active set (a vehicle waiting at a red light poses the same problem at every
+// step: certified in one or two rounds instead of being left to the robust pass every time).
 template <bool FIRST_PASS, class ST>
 MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, const ST& st, bool live,
                            const double* U_start = nullptr) {
   SolveOut out{MPCB_MAXITER, 0, 0, false};
   const bool screened = prologue(T, P, pb, st);
-  if (!FIRST_PASS && U_start) {
+  const bool hot = FIRST_PASS && U_start != nullptr;
+  if (U_start) {
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
       const double u = clipd(U_start[i], P.umin[i & 1], P.umax[i & 1]);
@@ -729,10 +733,18 @@ MPCB_HD SolveOut solve_one(const DevTable& T, const DevParams& P, Problem& pb, c
   auto cold_start = [&](const double (&xx)[NV]) {
 #pragma unroll
     for (int i = 0; i < 6; ++i) pb.E.w[i] = 0x11111111u * (unsigned)pl.e_init;
-    pb.act_prev = 0ull;
+    unsigned long long act0 = 0ull;
     for_rows(P, pb, st, xx, [&](int r, double zt, double lo, double hi, auto kind) {
-      st.v[r] = clipk<decltype(kind)::value>(zt, lo, hi);
+      constexpr int KIND = decltype(kind)::value;
+      st.v[r] = clipk<KIND>(zt, lo, hi);
+      // hot start (the controls come from a solution of a neighbouring problem, e.g. the previous time step's plan): a row
+      // that sits on its bound there starts as active, so the first segment is already a KKT solve on that active set
+      if (hot) {
+        const bool at_lo = (KIND != 2) && (zt <= lo + P.feas_tol), at_hi = (KIND != 1) && (zt >= hi - P.feas_tol);
+        if (at_lo || at_hi) act0 |= (1ull << r);
+      }
     });
+    pb.act_prev = act0;
   };
   for (int round = 0; round < max_rounds; ++round) {
     if (MPCB_ALL(done)) break;

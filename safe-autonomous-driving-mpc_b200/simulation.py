@@ -67,9 +67,10 @@ def check_histories(tracker, s_total, scenarios, x_final, steps, hist_x, hist_u,
 
 
 class BatchedSimulation:
-    def __init__(self, tracker, scenarios, B=None, x_init=None, history_steps=0):
+    def __init__(self, tracker, scenarios, B=None, x_init=None, history_steps=0, hot_start=False):
         """tracker: BatchedTracker; scenarios: one Scenario (shared) or a list of B; x_init: [B,5] or None for the
-        reference's start state."""
+        reference's start state.  hot_start: from its second step on a vehicle's solve starts from its previous plan
+        advanced by one step (mpcb_sim_set_hot_start) instead of the reference's table-based warm start."""
         self._lib = tracker._lib
         self._t = tracker
         scen = list(scenarios) if isinstance(scenarios, (list, tuple)) else [scenarios]
@@ -85,6 +86,8 @@ class BatchedSimulation:
         self._h = h
         self.B = int(B)
         self.history_steps = int(history_steps)
+        if hot_start:
+            check(self._lib.mpcb_sim_set_hot_start(h, 1), "mpcb_sim_set_hot_start")
 
     def __del__(self):
         h = getattr(self, "_h", None)

@@ -59,11 +59,13 @@ int host_hs_eval(const double* s, const double* y, int K, double dt, int simpson
 #ifdef MPCB_HOST_SOLVER
 #include "mpcb_params.h"
 
+static const double* g_hot_U = nullptr;   // development: [B][10] controls the FIRST pass starts from (instead of the warm start)
 static int* g_pass2_stats = nullptr;   // development: [B][3] rounds, iterations, status of the robust pass alone
 
 extern "C" {
 
 void host_set_pass2_stats(int* p) { g_pass2_stats = p; }
+void host_set_hot_start(const double* U) { g_hot_U = U; }
 
 // The tracking solver (solve_one, the code mpcb_solve_kernel runs per thread) on the CPU, one problem at a time,
 // with the same two-pass logic as launch_solve.  `p` may be null (defaults).  Outputs like mpcb_solve_batch;
@@ -91,7 +93,7 @@ int host_solve_batch(const double* s, const double* y, const double* u, int K, i
       typedef Store<1, 0u> HostStore;
       double buf[HostStore::LOCAL];
       HostStore st(nullptr, buf);
-      SolveOut so = (pass == 1) ? solve_one<true>(T, P, pb, st, true)
+      SolveOut so = (pass == 1) ? solve_one<true>(T, P, pb, st, true, g_hot_U ? g_hot_U + 10 * b : nullptr)
                                 : solve_one<false>(T, P, pb, st, true, (carry && have1) ? U1 : nullptr);
       rounds += so.rounds; iters += so.iters;
       if (pass == 2 && g_pass2_stats) { g_pass2_stats[3 * b] = so.rounds; g_pass2_stats[3 * b + 1] = so.iters; g_pass2_stats[3 * b + 2] = so.status; }

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/mpcb200.h but not exported"
         assert n in _lib.SYMBOLS, f"{n} has no ctypes signature"
-    assert lib.mpcb_abi_version() == 6
+    assert lib.mpcb_abi_version() == 7
     assert lib.mpcb_strerror(-1) == b"invalid argument"
 
 

@@ -188,3 +188,32 @@ def test_fleet_caps_drive_a_staggered_fleet_like_the_defaults(gpu_trackers):
     assert ca["passed"].mean() > 0.97 and cb["passed"].mean() > 0.97
     d = np.abs(sa - sb)[both]
     assert np.quantile(d, 0.99) <= 3 and d.max() <= 0.05 * sa.max(), (np.quantile(d, [0.5, 0.99]), d.max())
+
+
+@pytest.mark.parametrize("i", [1, 2, 3])
+def test_hot_start_drives_the_same_closed_loop(i, gpu_trackers):
+    """mpcb_sim_set_hot_start: from its second step on a vehicle's first pass starts from its previous plan advanced by one
+    step, rows on their bounds taken as active.  The problem and its converged answer are the same: the device loop takes
+    the reference's step counts (172 / 985 / 2294), passes the same checks and follows the default loop's states -- up to
+    the last 10 m of the route, where the horizon runs off the end of the table and the optimum is no longer unique
+    (envelope test)."""
+    import safe_autonomous_driving_mpc_b200 as M
+    L, T = gpu_trackers[i]
+    scen = M.make_scenario(2, dynamic_obstacle=0, traffic_light=0) if i == 1 else M.make_scenario(i)
+    want = {1: 172, 2: 985, 3: 2294}[i]
+    out = []
+    for hot in (False, True):
+        sim = M.BatchedSimulation(T, scen, B=4, history_steps=want + 8, hot_start=hot)
+        sim.run(max_steps=want + 8, check_every=64)
+        x, steps, uns = sim.state()
+        c = sim.check()
+        assert np.all(steps == want) and c["passed"].all() and c["history_complete"].all()
+        out.append((sim.history(), uns))
+    (ha, ua), (hb, ub) = out
+    assert np.abs(ua - ub).max() <= 3
+    far = ha["x"][:want, 0, 0] < L.s_max - 10.0
+    dx = np.abs(ha["x"][:want, 0] - hb["x"][:want, 0])[far]
+    # trajectory1 / 3: 1e-6 .. 1e-5.  trajectory2: 0.075 m / 1.2e-4 m / 0.027 m/s -- its red-light approach is infeasible
+    # for 70 steps in a row, and what an infeasible problem returns depends on the path the solver took (SURVEY 4.4-4:
+    # flags only there); the two loops rejoin behind the light
+    assert dx[:, 1].max() <= 5e-4 and dx[:, 2].max() <= 5e-4 and dx[:, 4].max() <= 0.05 and dx[:, 0].max() <= 0.1, dx.max(axis=0)

@@ -5,13 +5,17 @@ sys.path.insert(0, ROOT)
 import numpy as np, torch
 import safe_autonomous_driving_mpc_b200 as M
 kw = {}
+HOT = False
 for a in sys.argv[1:]:
     k, v = a.split("=")
-    kw[k] = int(v)
+    if k == "hot":
+        HOT = bool(int(v))
+    else:
+        kw[k] = int(v)
 print(kw)
 L = M.TrajectoryLoader(f"{ROOT}/data/trajectory3.npz"); T = M.BatchedTracker(L, **kw)
 rng = np.random.default_rng(11)
-for B in (65536,):
+for B in (4096, 65536):
     xi = np.zeros((B, 5))
     s0 = rng.uniform(0.0, L.s_max - 400.0, B)
     for b in range(B):
@@ -19,7 +23,7 @@ for B in (65536,):
     xi[:, 4] = np.clip(xi[:, 4], 0.5, None)
     scen = [M.make_scenario(3, tl_pos=float(s + rng.uniform(150, 350)), obs_trigger_s=float(s + 5), obs_start_s=float(s + 60),
                             obs_end_s=float(s + 300)) for s in s0]
-    sim = M.BatchedSimulation(T, scen, x_init=xi)
+    sim = M.BatchedSimulation(T, scen, x_init=xi, hot_start=HOT)
     sim.step(8); torch.cuda.synchronize()
     x0_, st0, _ = sim.state()
     t0 = time.perf_counter()
