@@ -21,7 +21,7 @@ for traj, which, tl_lo, tl_hi in ((2, 2, 450.0, 650.0), (3, 3, 300.0, 900.0)):
     base = M.make_scenario(which)
     scen = [M.make_scenario(which, obs_v=float(rng.uniform(3.0, 6.0)), tl_pos=float(rng.uniform(tl_lo, tl_hi)),
                             tl_stop_duration=float(rng.uniform(5.0, 25.0))) for _ in range(B)]
-    sim = M.BatchedSimulation(T, scen, B=B, x_init=x_init, history_steps=4000)
+    sim = M.BatchedSimulation(T, scen, B=B, x_init=x_init, history_steps=4000, hot_start=bool(int(os.environ.get("HOT", "0"))))
     t0 = time.perf_counter()
     sim.run(max_steps=4000, check_every=200)
     dt = time.perf_counter() - t0
