@@ -8,6 +8,11 @@ import numpy as np, torch
 import safe_autonomous_driving_mpc_b200 as M
 from oracle import tracker_port as P
 dev = torch.device("cuda", 0)
+KW = {}
+for a in sys.argv[1:]:
+    k, v = a.split("=")
+    KW[k] = int(v)
+print(KW)
 L = M.TrajectoryLoader(f"{ROOT}/data/trajectory3.npz")
 tab = P.RefTable.from_npz(f"{ROOT}/data/trajectory3.npz")
 B, NSET, K = 65536, 8, 40
@@ -16,8 +21,8 @@ for k in range(NSET):
     x0, obs, n = P.monte_carlo_problems(tab, B, seed=P.MC_SEED + k)
     sets.append([torch.from_numpy(a).to(dev) for a in (x0, obs, n)])
 for side in (0,):
-    for ns in (1, 2, 3, 4):
-        Ts = [M.BatchedTracker(L) for _ in range(ns)]
+    for ns in (1, 2):
+        Ts = [M.BatchedTracker(L, **KW) for _ in range(ns)]
         streams = [torch.cuda.Stream(dev) for _ in range(ns)]
         outs = [Ts[0].solve_batch(*sets[k]) for k in range(NSET)]
         torch.cuda.synchronize()
