@@ -64,10 +64,14 @@ def test_full_short_route_physical_sign(port_tables):
     assert np.all(np.diff(X[:, 0]) > -1e-2)          # the final approach may creep back by < 1 cm (v >= -0.1 tolerance)
 
 
+def ev_pack(X, U, S):
+    return np.concatenate([np.ravel(X), np.ravel(U), np.ravel(S)])
+
+
 @pytest.mark.gpu
 def test_gpu_evaluator_drives_the_same_solution(gpu_trackers, port_tables):
     """The CUDA evaluator behind the driver: the reference's chunk (objective as above) and the physical short route
-    (same verdicts, same trajectory as the CPU-oracle-driven run to 1e-6)."""
+    (passes the reference's checks; the evaluator agrees with the CPU oracle at every point of the plan)."""
     import safe_autonomous_driving_mpc_b200 as M
     from oracle import planner_port as Q
     D = _driver()
@@ -81,13 +85,17 @@ def test_gpu_evaluator_drives_the_same_solution(gpu_trackers, port_tables):
     s_total, v_max = 70.0, 8.0
     Xg, Ug, Sg, logg = D.optimize_full_trajectory(
         lambda n, st: M.PlannerEvaluator(T, N=n, simpson_sign=+1, s_total=st, v_max=v_max), s_total, v_max)
-    Xc, Uc, Sc, logc = D.optimize_full_trajectory(
-        lambda n, st: Q.OracleEvaluator(port_tables[1], n, simpson_sign=+1, s_total=st, v_max=v_max), s_total, v_max)
     assert all(D.reference_trajectory_verdicts(Xg, Ug, Sg, s_total).values())
-    # SLSQP stops at ftol = 1e-4 (the reference's setting), so rounding-level differences between the two evaluators move
-    # the accepted iterates a little; the trajectories agree to centimetres and the chunk costs to 2e-3 (measured: one
-    # chunk 1.4e-3 apart once the device code took sin and cos from one sincos call, 1 ulp from the separate calls)
-    assert Xg.shape == Xc.shape and np.abs(Xg - Xc).max() <= 5e-2 and np.abs(Ug - Uc).max() <= 5e-2
-    assert len(logg) == len(logc)
-    for a, b in zip(logg, logc):
-        assert a["N"] == b["N"] and abs(a["cost"] - b["cost"]) <= 2e-3 * max(1.0, abs(b["cost"]))
+    assert abs(Xg[-1, 0] - s_total) <= 1e-3 and abs(Xg[-1, 4]) <= 1e-3 and all(c["status"] == 0 for c in logg)
+    # The same route planned with the CPU oracle as the evaluator takes a different SLSQP path (ftol = 1e-4, the reference's
+    # setting: rounding-level differences between the evaluators move the accepted iterates, and on some host CPUs one of
+    # the two runs ends in a different local solution of a chunk), so the two PLANS are not compared.  What must agree is
+    # what the evaluators return at the same points -- here along the GPU-driven plan, window by window.
+    N = 12
+    for k0 in range(0, len(Ug) - N, N):
+        z = ev_pack(Xg[k0:k0 + N + 1], Ug[k0:k0 + N], Sg[k0:k0 + N])
+        eg = M.PlannerEvaluator(T, N=N, simpson_sign=+1, s_total=s_total, v_max=v_max).evaluate_host(z, want_jac=True)
+        ec = Q.OracleEvaluator(port_tables[1], N, simpson_sign=+1, s_total=s_total, v_max=v_max).evaluate_host(z, want_jac=True)
+        for key in ("defect", "jac", "node_rows", "ctrl_rows", "cost", "cost_grad"):
+            a, b = np.asarray(eg[key]), np.asarray(ec[key])
+            assert np.abs(a - b).max() <= 1e-9 * max(1.0, np.abs(b).max()), (key, k0)
